@@ -1,0 +1,163 @@
+/* b200ref.h -- C-ABI of the B200-native draw-comparison hot path.
+ *
+ * Drop-in boundary for mcmc-ref's diagnostics / stats / compare path.  The
+ * reference is pure Python and has no FFI; each entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ * The reference-side binding a maintainer would add is the ctypes stub shown in
+ * INTEGRATION.md (mirrored by mcmc-db_b200/mcmc_ref_b200/_native.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - "_dev" pointers are CUDA device pointers owned by the caller.  The library
+ *     never frees caller memory and allocates device memory only inside the
+ *     caller-supplied workspace `ws` (size from b200ref_workspace_bytes).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - calls are synchronous from the caller's view: they return after the work
+ *     on `stream` has completed (unless documented otherwise), so outputs are
+ *     valid on return.  ctypes releases the GIL during the call.
+ *   - return 0 on success, negative error code otherwise; the message is in
+ *     b200ref_last_error() (thread-local).
+ *   - canonical layout: x[P][C][N] fp64, draw index fastest (an Arrow/Parquet
+ *     parameter column with rows sorted chain-major is exactly one x[p]).
+ *   - non-finite input is rejected with B200REF_ERR_NONFINITE (documented
+ *     divergence: the reference's behaviour on NaN is order-dependent).
+ */
+#ifndef B200REF_H
+#define B200REF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REF_VERSION 100
+
+#define B200REF_OK 0
+#define B200REF_ERR_ARG (-1)        /* bad shape / null pointer / nq too large   */
+#define B200REF_ERR_WORKSPACE (-2)  /* workspace too small                        */
+#define B200REF_ERR_CUDA (-3)       /* a CUDA runtime call or kernel failed       */
+#define B200REF_ERR_NONFINITE (-4)  /* NaN or +-inf in the input draws            */
+
+#define B200REF_MAX_QUANTILES 8
+
+/* Output block of the fused pass: struct-of-arrays, each [P] unless noted.
+ * Any pointer may be NULL (that output is skipped).  All device pointers. */
+typedef struct b200ref_outputs {
+  double* rhat;        /* max(rhat_bulk, rhat_folded)  -- diagnostics.py:13-40   */
+  double* rhat_bulk;   /* _rhat(split(rank_normalize(x)))                         */
+  double* rhat_tail;   /* _rhat(split(rank_normalize(fold(x))))                   */
+  double* ess_bulk;    /* diagnostics.py:43-56                                    */
+  double* ess_tail;    /* diagnostics.py:59-73                                    */
+  int64_t* lag_bulk;   /* first lag with rho < 0 (n if none) -- diagnostics.py:172-176 */
+  int64_t* lag_tail;
+  double* mean;        /* compare.py:58-64 / backends_numpy.py:41                 */
+  double* std;         /* population std (ddof = 0)                               */
+  double* quantiles;   /* [P][nq] numpy-linear -- backends_numpy.py:44            */
+  double* order_stats; /* [P][nq][2] the two selected order statistics s[lo], s[lo+1] */
+  double* median;      /* pooled statistics.median -- diagnostics.py:97           */
+} b200ref_outputs;
+
+/* Version of this ABI (B200REF_VERSION). */
+int b200ref_version(void);
+
+/* Message of the last error on this thread ("" if none). */
+const char* b200ref_last_error(void);
+
+/* Number of sm_100a kernels this library has launched in this process
+ * (monotone counter; bench.py reports the delta over its timed region). */
+uint64_t b200ref_kernel_launches(void);
+
+/* Workspace needed to process P parameters of C chains x N draws in one call
+ * (the library loops over parameter batches internally if given less, down to
+ * the size of one batch; see b200ref_workspace_min_bytes). */
+size_t b200ref_workspace_bytes(int64_t P, int64_t C, int64_t N);
+size_t b200ref_workspace_min_bytes(int64_t C, int64_t N);
+
+/* Pooled average ranks and normal scores of x and of fold(x).
+ * Replaces _rank_normalize (diagnostics.py:101-133) and _fold_chains (:93-98).
+ * Outputs [P][C][N] in the original positions; any may be NULL.
+ * Ranks are exact (half-integers); z follows AS241 in the stdlib's operation order. */
+int b200ref_ranks_f64(const double* x_dev, int64_t P, int64_t C, int64_t N,
+                      double* avg_rank_dev, double* z_dev,
+                      double* avg_rank_folded_dev, double* z_folded_dev,
+                      void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Rank-normalised split R-hat, bulk ESS, folded ("tail") ESS, plus pooled
+ * mean/std/quantiles of x, for P parameters.
+ * Replaces split_rhat / ess_bulk / ess_tail (diagnostics.py:13-73) and the
+ * per-column body of NumpyBackend.stats (backends_numpy.py:40-47) /
+ * compute_basic_stats (compare.py:58-64).
+ * q_host: nq quantile levels in [0,1] (host pointer, nq <= B200REF_MAX_QUANTILES). */
+int b200ref_diagnostics_f64(const double* x_dev, int64_t P, int64_t C, int64_t N,
+                            const double* q_host, int nq, const b200ref_outputs* out,
+                            void* ws_dev, size_t ws_bytes, void* stream);
+
+/* mean / std(ddof=0) / numpy-linear quantiles over the pooled M draws of each of
+ * P parameters; no diagnostics.  Replaces NumpyBackend.stats (backends_numpy.py:17-49).
+ * Only out->mean, std, quantiles, order_stats, median are written. */
+int b200ref_stats_f64(const double* x_dev, int64_t P, int64_t M,
+                      const double* q_host, int nq, const b200ref_outputs* out,
+                      void* ws_dev, size_t ws_bytes, void* stream);
+
+/* rel = |act - ref| / max(|ref|, 1e-12);  passed = rel <= tol (NaN fails).
+ * Replaces the inner loop of compare_stats (compare.py:38-43) over n values.
+ * all_passed_dev (optional, 1 byte) receives the AND of passed[]. */
+int b200ref_compare_f64(const double* ref_dev, const double* act_dev, int64_t n, double tol,
+                        double* rel_err_dev, uint8_t* passed_dev, uint8_t* all_passed_dev,
+                        void* stream);
+
+/* Quality-gate verdicts of convert._checks (convert.py:164-172) over P parameters:
+ * verdicts_host[0] = all(ess_bulk > 400), verdicts_host[1] = all(rhat < 1.01). */
+int b200ref_checks_f64(const double* rhat_dev, const double* ess_bulk_dev, int64_t P,
+                       uint8_t* verdicts_host, void* stream);
+
+/* HOST-buffer form of the full diagnostics + compare pass (the end-to-end call).
+ * cand_host [P][C][N] candidate draws and ref_host [P][Mref] reference draws are
+ * host buffers (pinned for full speed); the library stages them through the
+ * workspace in parameter batches, overlapping H2D copies with kernels, and
+ * writes host outputs:
+ *   out_host   [P][B200REF_SUMMARY_K] doubles, see B200REF_S_* below
+ * Replaces reference.compare + diagnostics_for_model's per-parameter loop
+ * (reference.py:76-122).  Returns the overall compare verdict in *passed_host. */
+#define B200REF_SUMMARY_K 16
+#define B200REF_S_RHAT 0
+#define B200REF_S_ESS_BULK 1
+#define B200REF_S_ESS_TAIL 2
+#define B200REF_S_MEAN 3
+#define B200REF_S_STD 4
+#define B200REF_S_Q5 5
+#define B200REF_S_Q50 6
+#define B200REF_S_Q95 7
+#define B200REF_S_REF_MEAN 8
+#define B200REF_S_REF_STD 9
+#define B200REF_S_REF_Q5 10
+#define B200REF_S_REF_Q50 11
+#define B200REF_S_REF_Q95 12
+#define B200REF_S_REL_MEAN 13
+#define B200REF_S_REL_STD 14
+#define B200REF_S_FLAGS 15 /* bit0 mean passed, bit1 std passed (stored as double) */
+
+/* Device-resident form: inputs already in HBM, summary written to device. */
+int b200ref_full_pass_f64(const double* cand_dev, int64_t P, int64_t C, int64_t N,
+                          const double* ref_dev, int64_t Mref, double tol,
+                          double* summary_dev /* [P][16] */, uint8_t* passed_host,
+                          void* ws_dev, size_t ws_bytes, void* stream);
+
+int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, int64_t N,
+                               const double* ref_host, int64_t Mref, double tol,
+                               double* summary_host /* [P][16] */, uint8_t* passed_host,
+                               void* ws_dev, size_t ws_bytes);
+
+/* Synthetic workload of SURVEY.md 8(d) (bench/test utility, not on the hot path):
+ * x[p][c][i] = mu_p + sigma_p * AR1(phi_p), counter-based on (seed, p0 + p, c, i)
+ * so values do not depend on tiling or GPU count.  kind 0 = candidate [P][C][N],
+ * kind 1 = reference posterior [P][C][N] iid (every 89th param mean-shifted). */
+int b200ref_synth_fill_f64(double* x_dev, int64_t p0, int64_t P, int64_t C, int64_t N,
+                           uint64_t seed, int kind, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REF_H */

@@ -1,0 +1,572 @@
+// C-ABI of libb200ref.so (declared in include/b200ref.h): host orchestration of the
+// sm_100a kernels for mcmc-ref's diagnostics / stats / compare path.
+#include "../../include/b200ref.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+
+#include "as241.cuh"
+#include "chain.cuh"
+#include "common.cuh"
+#include "rank.cuh"
+#include "sort.cuh"
+#include "synth.cuh"
+
+using namespace b200ref;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(B200REF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),  \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+constexpr size_t ALIGN = 256;
+inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
+
+// Workspace carve-up for one batch of PB parameters with M pooled draws each.
+struct Layout {
+  size_t ztab, flag, header;  // shared part
+  size_t key0, key1, idx0, idx1, zb, zf, hist, sel, sum, med, m0, apos, sqpart, crhat, cess, clag, per_batch;
+  uint32_t ntiles;
+  void compute(int64_t PB, int64_t M, bool diag) {
+    ntiles = (uint32_t)((M + RANK_TILE - 1) / RANK_TILE);
+    size_t o = 0;
+    ztab = o; o += up(2 * (size_t)M * sizeof(double));
+    flag = o; o += up(sizeof(int));
+    header = o;
+    size_t b = 0;
+    const size_t n = (size_t)PB * (size_t)M;
+    key0 = b; b += up(n * 8);
+    key1 = b; b += up(n * 8);
+    idx0 = b; b += up(n * 4);
+    idx1 = b; b += up(n * 4);
+    zb = b; b += diag ? up(n * 8) : 0;
+    zf = b; b += diag ? up(n * 8) : 0;
+    hist = b; b += up((size_t)PB * 8 * 256 * 4);
+    sel = b; b += up((size_t)PB * 4);
+    sum = b; b += up((size_t)PB * 8);
+    med = b; b += up((size_t)PB * 8);
+    m0 = b; b += up((size_t)PB * 4);
+    apos = b; b += up((size_t)PB * (ntiles + 1) * 4);
+    sqpart = b; b += up((size_t)PB * ntiles * 8);
+    crhat = b; b += up((size_t)PB * 2 * 8);
+    cess = b; b += up((size_t)PB * 2 * 8);
+    clag = b; b += up((size_t)PB * 2 * 8);
+    per_batch = b;
+  }
+};
+
+// Largest batch (<= P) whose layout fits in ws_bytes; 0 if not even one parameter fits.
+int64_t fit_batch(int64_t P, int64_t M, bool diag, size_t ws_bytes, int64_t cap) {
+  int64_t hi = std::min<int64_t>(P, cap), lo = 0;
+  Layout l;
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo + 1) / 2;
+    l.compute(mid, M, diag);
+    if (l.header + l.per_batch <= ws_bytes) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+constexpr int64_t BATCH_CAP = 4096;
+
+// ---- small kernels used only by the orchestration ----
+
+__global__ void k_sumsq(const double* __restrict__ x, uint32_t M, uint32_t ntiles, const double* __restrict__ sum,
+                        double* __restrict__ sqpart) {
+  __shared__ double red[33];
+  const int p = blockIdx.y;
+  const uint32_t base = blockIdx.x * RANK_TILE;
+  const double mean = sum[p] / (double)M;
+  const double* xp = x + (size_t)p * M;
+  double sq = 0.0;
+  for (uint32_t e = base + threadIdx.x; e < min(base + (uint32_t)RANK_TILE, M); e += RANK_NT) {
+    const double d = xp[e] - mean;
+    sq += d * d;
+  }
+  sq = block_sum<RANK_NT>(sq, red);
+  if (threadIdx.x == 0) sqpart[(size_t)p * ntiles + blockIdx.x] = sq;
+}
+
+struct FinalizeArgs {
+  const double* sum;      // [PB]
+  const double* sqpart;   // [PB][ntiles]
+  const double* crhat;    // [2][PB] or null
+  const double* cess;     // [2][PB]
+  const long long* clag;  // [2][PB]
+  uint32_t ntiles;
+  double* std_out;        // [PB] or null (already offset to this batch)
+  double* rhat;           // or null
+  double* rhat_bulk;
+  double* rhat_tail;
+  double* ess_bulk;
+  double* ess_tail;
+  int64_t* lag_bulk;
+  int64_t* lag_tail;
+};
+
+__global__ void k_finalize(FinalizeArgs a, uint32_t M, int PB) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= PB) return;
+  if (a.std_out) {
+    double s = 0.0;
+    for (uint32_t t = 0; t < a.ntiles; ++t) s += a.sqpart[(size_t)p * a.ntiles + t];
+    a.std_out[p] = sqrt(s / (double)M);
+  }
+  if (a.crhat) {
+    const double rb = a.crhat[p], rt = a.crhat[(size_t)PB + p];
+    // Python max(rb, rt): keeps rb unless rt > rb (diagnostics.py:40)
+    if (a.rhat) a.rhat[p] = (rt > rb) ? rt : rb;
+    if (a.rhat_bulk) a.rhat_bulk[p] = rb;
+    if (a.rhat_tail) a.rhat_tail[p] = rt;
+    if (a.ess_bulk) a.ess_bulk[p] = a.cess[p];
+    if (a.ess_tail) a.ess_tail[p] = a.cess[(size_t)PB + p];
+    if (a.lag_bulk) a.lag_bulk[p] = a.clag[p];
+    if (a.lag_tail) a.lag_tail[p] = a.clag[(size_t)PB + p];
+  }
+}
+
+// compare_stats inner loop (compare.py:39-43)
+__global__ void k_compare(const double* __restrict__ ref, const double* __restrict__ act, int64_t n, double tol,
+                          double* __restrict__ rel, uint8_t* __restrict__ passed, int* __restrict__ nfail) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = ref[i], a = act[i];
+  // Python max(abs(r), 1e-12): keeps abs(r) unless 1e-12 > abs(r)  (NaN stays NaN)
+  const double ar = fabs(r);
+  const double denom = (1e-12 > ar) ? 1e-12 : ar;
+  const double e = __ddiv_rn(fabs(__dsub_rn(a, r)), denom);
+  const bool ok = e <= tol;
+  if (rel) rel[i] = e;
+  if (passed) passed[i] = ok ? 1 : 0;
+  if (!ok && nfail) atomicAdd(nfail, 1);
+}
+
+// _checks (convert.py:165-166): counts of violations
+__global__ void k_checks(const double* __restrict__ rhat, const double* __restrict__ essb, int64_t P, int* viol) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  if (!(essb[i] > 400.0)) atomicAdd(&viol[0], 1);
+  if (!(rhat[i] < 1.01)) atomicAdd(&viol[1], 1);
+}
+
+// Summary rows [P][16] of the fused pass (include/b200ref.h B200REF_S_*).
+__global__ void k_summary(const double* rhat, const double* essb, const double* esst, const double* mean,
+                          const double* sd, const double* q, const double* rmean, const double* rsd,
+                          const double* rq, double tol, int64_t P, double* out, int* nfail) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double* o = out + p * B200REF_SUMMARY_K;
+  o[B200REF_S_RHAT] = rhat[p];
+  o[B200REF_S_ESS_BULK] = essb[p];
+  o[B200REF_S_ESS_TAIL] = esst[p];
+  o[B200REF_S_MEAN] = mean[p];
+  o[B200REF_S_STD] = sd[p];
+  o[B200REF_S_Q5] = q[p * 3 + 0];
+  o[B200REF_S_Q50] = q[p * 3 + 1];
+  o[B200REF_S_Q95] = q[p * 3 + 2];
+  o[B200REF_S_REF_MEAN] = rmean[p];
+  o[B200REF_S_REF_STD] = rsd[p];
+  o[B200REF_S_REF_Q5] = rq[p * 3 + 0];
+  o[B200REF_S_REF_Q50] = rq[p * 3 + 1];
+  o[B200REF_S_REF_Q95] = rq[p * 3 + 2];
+  int flags = 0;
+  {
+    const double ar = fabs(rmean[p]);
+    const double e = __ddiv_rn(fabs(__dsub_rn(mean[p], rmean[p])), (1e-12 > ar) ? 1e-12 : ar);
+    o[B200REF_S_REL_MEAN] = e;
+    if (e <= tol) flags |= 1;
+  }
+  {
+    const double ar = fabs(rsd[p]);
+    const double e = __ddiv_rn(fabs(__dsub_rn(sd[p], rsd[p])), (1e-12 > ar) ? 1e-12 : ar);
+    o[B200REF_S_REL_STD] = e;
+    if (e <= tol) flags |= 2;
+  }
+  o[B200REF_S_FLAGS] = (double)flags;
+  if (flags != 3) atomicAdd(nfail, 1);
+}
+
+struct Mode {
+  bool diag;         // run fold + chain kernels
+  bool want_ranks;   // scatter average ranks (ranks API)
+};
+
+// Process P parameters in batches.  `x` [P][M]; outputs are offset per batch.
+int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, int nq, const b200ref_outputs* out,
+        double* rank_b, double* z_b, double* rank_f, double* z_f, Mode mode, void* ws, size_t ws_bytes,
+        cudaStream_t st) {
+  const int64_t M = C * N;
+  if (!x || P < 0 || C < 1 || N < 1) return fail(B200REF_ERR_ARG, "bad shape P=%lld C=%lld N=%lld", (long long)P,
+                                                 (long long)C, (long long)N);
+  if (M >= (1ll << 31)) return fail(B200REF_ERR_ARG, "C*N = %lld exceeds 2^31-1", (long long)M);
+  if (nq < 0 || nq > B200REF_MAX_QUANTILES) return fail(B200REF_ERR_ARG, "nq=%d out of range", nq);
+  if (P == 0) return B200REF_OK;
+  if (!ws) return fail(B200REF_ERR_WORKSPACE, "null workspace");
+  size_t chain_smem = 0;
+  if (mode.diag) {
+    chain_smem = chain_smem_bytes(C, N);
+    if (chain_smem > 227 * 1024)
+      return fail(B200REF_ERR_ARG, "N=%lld draws per chain does not fit the on-chip chain buffer", (long long)N);
+    CUDA_TRY(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));
+  }
+  const bool need_z = mode.diag;
+  const int64_t PBmax = fit_batch(P, M, need_z && !z_b, ws_bytes, BATCH_CAP);
+  if (PBmax < 1) return fail(B200REF_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one parameter", ws_bytes);
+  Layout L;
+  L.compute(PBmax, M, need_z && !z_b);
+  char* w = (char*)ws;
+  double* ztab = (double*)(w + L.ztab);
+  int* flag = (int*)(w + L.flag);
+  char* wb = w + L.header;
+
+  CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  if (need_z || z_b || z_f) {
+    k_ztable<<<296, 256, 0, st>>>(ztab, (uint32_t)M);
+    LAUNCHED();
+  }
+  QuantArgs qa;
+  qa.nq = nq;
+  for (int i = 0; i < nq; ++i) qa.q[i] = q_host[i];
+
+  for (int64_t p0 = 0; p0 < P; p0 += PBmax) {
+    const int PB = (int)std::min<int64_t>(PBmax, P - p0);
+    const double* xb = x + (size_t)p0 * M;
+    SortBufs sb;
+    sb.key[0] = (uint64_t*)(wb + L.key0);
+    sb.key[1] = (uint64_t*)(wb + L.key1);
+    sb.idx[0] = (uint32_t*)(wb + L.idx0);
+    sb.idx[1] = (uint32_t*)(wb + L.idx1);
+    sb.hist = (uint32_t*)(wb + L.hist);
+    sb.sel = (int*)(wb + L.sel);
+    sb.sum = (double*)(wb + L.sum);
+    sb.flag = flag;
+    k_hist0<<<PB, 1024, 0, st>>>(xb, (uint32_t)M, sb);
+    LAUNCHED();
+    k_radix_pass<true><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, 0, sb);
+    LAUNCHED();
+    for (int pass = 1; pass < 8; ++pass) {
+      k_radix_pass<false><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, pass, sb);
+      LAUNCHED();
+    }
+    RankBufs rb;
+    rb.key[0] = sb.key[0]; rb.key[1] = sb.key[1];
+    rb.idx[0] = sb.idx[0]; rb.idx[1] = sb.idx[1];
+    rb.sel = sb.sel;
+    rb.sum = sb.sum;
+    rb.med = (double*)(wb + L.med);
+    rb.m0 = (uint32_t*)(wb + L.m0);
+    rb.apos = (uint32_t*)(wb + L.apos);
+    rb.sqpart = (double*)(wb + L.sqpart);
+    rb.ztab = ztab;
+    PrepOut po;
+    po.quant = (out && out->quantiles) ? out->quantiles + (size_t)p0 * nq : nullptr;
+    po.ostats = (out && out->order_stats) ? out->order_stats + (size_t)p0 * nq * 2 : nullptr;
+    po.median = (out && out->median) ? out->median + p0 : nullptr;
+    po.mean = (out && out->mean) ? out->mean + p0 : nullptr;
+    k_param_prep<<<(PB + 127) / 128, 128, 0, st>>>(rb, (uint32_t)M, PB, qa, po);
+    LAUNCHED();
+
+    const dim3 gt(L.ntiles, PB);
+    const bool ranks = mode.diag || mode.want_ranks;
+    double* zb = z_b ? z_b + (size_t)p0 * M : (need_z ? (double*)(wb + L.zb) : nullptr);
+    double* zf = z_f ? z_f + (size_t)p0 * M : (need_z ? (double*)(wb + L.zf) : nullptr);
+    if (ranks) {
+      ScatterOut so{zb, rank_b ? rank_b + (size_t)p0 * M : nullptr};
+      k_rank<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, so);
+      LAUNCHED();
+      if (mode.diag || zf || rank_f) {
+        k_merge_partition<<<dim3((L.ntiles + 1 + 127) / 128, PB), 128, 0, st>>>(rb, (uint32_t)M, L.ntiles, PB);
+        LAUNCHED();
+        ScatterOut sf{zf, rank_f ? rank_f + (size_t)p0 * M : nullptr};
+        k_fold<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, sf);
+        LAUNCHED();
+      }
+    } else {
+      k_sumsq<<<gt, RANK_NT, 0, st>>>(xb, (uint32_t)M, L.ntiles, sb.sum, rb.sqpart);
+      LAUNCHED();
+    }
+    ChainOut co{(double*)(wb + L.crhat), (double*)(wb + L.cess), (int64_t*)(wb + L.clag)};
+    if (mode.diag) {
+      k_chain<<<dim3(PB, 2), CH_NT, chain_smem, st>>>(zb, zf, (uint32_t)C, (uint32_t)N, PB, co);
+      LAUNCHED();
+    }
+    if (out) {
+      FinalizeArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.sum = sb.sum;
+      fa.sqpart = rb.sqpart;
+      fa.ntiles = L.ntiles;
+      fa.std_out = out->std ? out->std + p0 : nullptr;
+      if (mode.diag) {
+        fa.crhat = co.rhat;
+        fa.cess = co.ess;
+        fa.clag = (const long long*)co.lag;
+        fa.rhat = out->rhat ? out->rhat + p0 : nullptr;
+        fa.rhat_bulk = out->rhat_bulk ? out->rhat_bulk + p0 : nullptr;
+        fa.rhat_tail = out->rhat_tail ? out->rhat_tail + p0 : nullptr;
+        fa.ess_bulk = out->ess_bulk ? out->ess_bulk + p0 : nullptr;
+        fa.ess_tail = out->ess_tail ? out->ess_tail + p0 : nullptr;
+        fa.lag_bulk = out->lag_bulk ? out->lag_bulk + p0 : nullptr;
+        fa.lag_tail = out->lag_tail ? out->lag_tail + p0 : nullptr;
+      }
+      k_finalize<<<(PB + 127) / 128, 128, 0, st>>>(fa, (uint32_t)M, PB);
+      LAUNCHED();
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  int hflag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (hflag & 1) return fail(B200REF_ERR_NONFINITE, "non-finite value (NaN or inf) in input draws");
+  return B200REF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200ref_version(void) { return B200REF_VERSION; }
+const char* b200ref_last_error(void) { return g_err; }
+uint64_t b200ref_kernel_launches(void) { return g_launches.load(); }
+
+size_t b200ref_workspace_bytes(int64_t P, int64_t C, int64_t N) {
+  if (P < 1) P = 1;
+  Layout l;
+  l.compute(std::min<int64_t>(P, BATCH_CAP), C * N, true);
+  return l.header + l.per_batch;
+}
+size_t b200ref_workspace_min_bytes(int64_t C, int64_t N) {
+  Layout l;
+  l.compute(1, C * N, true);
+  return l.header + l.per_batch;
+}
+
+int b200ref_ranks_f64(const double* x, int64_t P, int64_t C, int64_t N, double* avg_rank, double* z,
+                      double* avg_rank_folded, double* z_folded, void* ws, size_t ws_bytes, void* stream) {
+  g_err[0] = 0;
+  Mode m{false, true};
+  return run(x, P, C, N, nullptr, 0, nullptr, avg_rank, z, avg_rank_folded, z_folded, m, ws, ws_bytes,
+             (cudaStream_t)stream);
+}
+
+int b200ref_diagnostics_f64(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, int nq,
+                            const b200ref_outputs* out, void* ws, size_t ws_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!out) return fail(B200REF_ERR_ARG, "null outputs");
+  if (nq > 0 && !q_host) return fail(B200REF_ERR_ARG, "null quantile levels");
+  Mode m{true, false};
+  return run(x, P, C, N, q_host, nq, out, nullptr, nullptr, nullptr, nullptr, m, ws, ws_bytes,
+             (cudaStream_t)stream);
+}
+
+int b200ref_stats_f64(const double* x, int64_t P, int64_t M, const double* q_host, int nq,
+                      const b200ref_outputs* out, void* ws, size_t ws_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!out) return fail(B200REF_ERR_ARG, "null outputs");
+  if (nq > 0 && !q_host) return fail(B200REF_ERR_ARG, "null quantile levels");
+  Mode m{false, false};
+  return run(x, P, 1, M, q_host, nq, out, nullptr, nullptr, nullptr, nullptr, m, ws, ws_bytes,
+             (cudaStream_t)stream);
+}
+
+int b200ref_compare_f64(const double* ref, const double* act, int64_t n, double tol, double* rel_err,
+                        uint8_t* passed, uint8_t* all_passed_dev, void* stream) {
+  g_err[0] = 0;
+  if (n < 0 || (n > 0 && (!ref || !act))) return fail(B200REF_ERR_ARG, "bad compare arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* nfail = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&nfail, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(nfail, 0, sizeof(int), st));
+  if (n > 0) {
+    k_compare<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ref, act, n, tol, rel_err, passed, nfail);
+    LAUNCHED();
+  }
+  int h = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h, nfail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (all_passed_dev) {
+    const uint8_t v = (h == 0) ? 1 : 0;
+    CUDA_TRY(cudaMemcpyAsync(all_passed_dev, &v, 1, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  CUDA_TRY(cudaFreeAsync(nfail, st));
+  CUDA_TRY(cudaGetLastError());
+  return B200REF_OK;
+}
+
+int b200ref_checks_f64(const double* rhat, const double* essb, int64_t P, uint8_t* verdicts_host, void* stream) {
+  g_err[0] = 0;
+  if (P < 0 || !verdicts_host || (P > 0 && (!rhat || !essb))) return fail(B200REF_ERR_ARG, "bad checks arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* viol = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&viol, 2 * sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(viol, 0, 2 * sizeof(int), st));
+  if (P > 0) {
+    k_checks<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(rhat, essb, P, viol);
+    LAUNCHED();
+  }
+  int h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h, viol, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaFreeAsync(viol, st));
+  verdicts_host[0] = h[0] == 0;
+  verdicts_host[1] = h[1] == 0;
+  return B200REF_OK;
+}
+
+// Scratch for the fused pass, carved from the END of the workspace:
+//   per-parameter result columns (13 doubles) + nfail.
+static size_t fused_tail_bytes(int64_t P) { return up((size_t)P * 13 * 8) + up(16); }
+
+int b200ref_full_pass_f64(const double* cand, int64_t P, int64_t C, int64_t N, const double* ref, int64_t Mref,
+                          double tol, double* summary, uint8_t* passed_host, void* ws, size_t ws_bytes,
+                          void* stream) {
+  g_err[0] = 0;
+  if (!cand || !ref || !summary || P < 1 || Mref < 1) return fail(B200REF_ERR_ARG, "bad full_pass arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t tail = fused_tail_bytes(P);
+  if (ws_bytes <= tail) return fail(B200REF_ERR_WORKSPACE, "workspace too small");
+  const size_t body = (ws_bytes - tail) / ALIGN * ALIGN;
+  double* cols = (double*)((char*)ws + body);
+  int* nfail = (int*)((char*)cols + up((size_t)P * 13 * 8));
+  double *rhat = cols, *essb = cols + P, *esst = cols + 2 * P, *mean = cols + 3 * P, *sd = cols + 4 * P,
+         *q = cols + 5 * P, *rmean = cols + 8 * P, *rsd = cols + 9 * P, *rq = cols + 10 * P;
+  const double qs[3] = {0.05, 0.5, 0.95};
+  b200ref_outputs oc;
+  memset(&oc, 0, sizeof(oc));
+  oc.rhat = rhat; oc.ess_bulk = essb; oc.ess_tail = esst; oc.mean = mean; oc.std = sd; oc.quantiles = q;
+  int rc = run(cand, P, C, N, qs, 3, &oc, nullptr, nullptr, nullptr, nullptr, Mode{true, false}, ws, body, st);
+  if (rc) return rc;
+  b200ref_outputs orf;
+  memset(&orf, 0, sizeof(orf));
+  orf.mean = rmean; orf.std = rsd; orf.quantiles = rq;
+  rc = run(ref, P, 1, Mref, qs, 3, &orf, nullptr, nullptr, nullptr, nullptr, Mode{false, false}, ws, body, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(nfail, 0, sizeof(int), st));
+  k_summary<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(rhat, essb, esst, mean, sd, q, rmean, rsd, rq, tol, P,
+                                                         summary, nfail);
+  LAUNCHED();
+  int h = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h, nfail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (passed_host) *passed_host = (h == 0) ? 1 : 0;
+  return B200REF_OK;
+}
+
+int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, int64_t N, const double* ref_host,
+                               int64_t Mref, double tol, double* summary_host, uint8_t* passed_host, void* ws,
+                               size_t ws_bytes) {
+  g_err[0] = 0;
+  if (!cand_host || !ref_host || !summary_host || P < 1) return fail(B200REF_ERR_ARG, "bad full_pass_host arguments");
+  // Stage inputs in parameter slabs: two slabs in flight, H2D of slab k+1 on the copy
+  // stream overlaps the kernels of slab k on the compute stream.
+  const int64_t M = C * N;
+  const size_t per_param_in = ((size_t)M + (size_t)Mref + B200REF_SUMMARY_K) * 8;
+  cudaStream_t s_copy, s_comp;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+  // split: 2 input slabs + a compute workspace sized for one slab
+  int64_t slab = std::min<int64_t>(P, 1024);
+  size_t need = 0;
+  for (; slab >= 1; slab = (slab > 1) ? slab / 2 : 0) {
+    need = 2 * up(per_param_in * slab) + b200ref_workspace_bytes(slab, C, N) + fused_tail_bytes(slab) + ALIGN;
+    if (need <= ws_bytes) break;
+  }
+  int rc = B200REF_OK;
+  if (slab < 1) {
+    rc = fail(B200REF_ERR_WORKSPACE, "workspace too small for host staging");
+  } else {
+    char* base = (char*)ws;
+    char* in[2] = {base, base + up(per_param_in * slab)};
+    char* cws = base + 2 * up(per_param_in * slab);
+    const size_t cws_bytes = ws_bytes - 2 * up(per_param_in * slab);
+    cudaEvent_t copied[2], computed[2];
+    for (int i = 0; i < 2; ++i) {
+      cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming);
+    }
+    uint8_t all_ok = 1;
+    const int64_t nslabs = (P + slab - 1) / slab;
+    auto issue_copy = [&](int64_t k) {
+      const int b = (int)(k & 1);
+      const int64_t p0 = k * slab, pb = std::min<int64_t>(slab, P - p0);
+      double* dc = (double*)in[b];
+      double* dr = dc + (size_t)slab * M;
+      cudaStreamWaitEvent(s_copy, computed[b], 0);
+      cudaMemcpyAsync(dc, cand_host + (size_t)p0 * M, (size_t)pb * M * 8, cudaMemcpyHostToDevice, s_copy);
+      cudaMemcpyAsync(dr, ref_host + (size_t)p0 * Mref, (size_t)pb * Mref * 8, cudaMemcpyHostToDevice, s_copy);
+      cudaEventRecord(copied[b], s_copy);
+    };
+    issue_copy(0);
+    for (int64_t k = 0; k < nslabs && rc == B200REF_OK; ++k) {
+      const int b = (int)(k & 1);
+      const int64_t p0 = k * slab, pb = std::min<int64_t>(slab, P - p0);
+      if (k + 1 < nslabs) issue_copy(k + 1);
+      double* dc = (double*)in[b];
+      double* dr = dc + (size_t)slab * M;
+      double* dsum = dr + (size_t)slab * Mref;
+      cudaStreamWaitEvent(s_comp, copied[b], 0);
+      uint8_t ok = 0;
+      rc = b200ref_full_pass_f64(dc, pb, C, N, dr, Mref, tol, dsum, &ok, cws, cws_bytes, s_comp);
+      if (rc) break;
+      all_ok &= ok;
+      cudaMemcpyAsync(summary_host + (size_t)p0 * B200REF_SUMMARY_K, dsum, (size_t)pb * B200REF_SUMMARY_K * 8,
+                      cudaMemcpyDeviceToHost, s_comp);
+      cudaEventRecord(computed[b], s_comp);
+    }
+    cudaStreamSynchronize(s_comp);
+    cudaStreamSynchronize(s_copy);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(copied[i]);
+      cudaEventDestroy(computed[i]);
+    }
+    if (rc == B200REF_OK) {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) rc = fail(B200REF_ERR_CUDA, "host pass failed: %s", cudaGetErrorString(e));
+      if (passed_host) *passed_host = all_ok;
+    }
+  }
+  cudaStreamDestroy(s_copy);
+  cudaStreamDestroy(s_comp);
+  return rc;
+}
+
+int b200ref_synth_fill_f64(double* x, int64_t p0, int64_t P, int64_t C, int64_t N, uint64_t seed, int kind,
+                           void* stream) {
+  g_err[0] = 0;
+  if (!x || P < 0 || C < 1 || N < 1) return fail(B200REF_ERR_ARG, "bad synth arguments");
+  if (P == 0) return B200REF_OK;
+  const int64_t nchains = P * C;
+  const int warps_per_block = 8;
+  const unsigned blocks = (unsigned)((nchains + warps_per_block - 1) / warps_per_block);
+  k_synth<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(x, p0, P, C, N, seed, kind);
+  LAUNCHED();
+  CUDA_TRY(cudaGetLastError());
+  return B200REF_OK;
+}
+
+}  // extern "C"

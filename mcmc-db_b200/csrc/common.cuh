@@ -1,0 +1,98 @@
+// Shared device helpers for the b200ref kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200ref {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// Order-preserving map double -> uint64.  -0.0 is canonicalised to +0.0 first
+// because the reference groups ties with Python `==` (diagnostics.py:116), under
+// which -0.0 == 0.0.  Inputs are finite (checked by the first kernel).
+__device__ __forceinline__ uint64_t dbl2key(double v) {
+  uint64_t u = (uint64_t)__double_as_longlong(v);
+  if (u == 0x8000000000000000ull) u = 0ull;
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key2dbl(uint64_t k) {
+  uint64_t u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ bool is_finite_bits(double v) {
+  return (((uint64_t)__double_as_longlong(v) >> 52) & 0x7ffull) != 0x7ffull;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in every thread.  `red` needs >= 33 doubles.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = (lane < NT / 32) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// Inclusive forward max-scan / reverse min-scan of one uint32 per (thread, item),
+// blocked arrangement (thread t owns positions t*IPT .. t*IPT+IPT-1).
+// `sm` needs NT/32 uint32.
+template <int NT, int IPT>
+__device__ __forceinline__ void block_scan_max_fwd(uint32_t (&v)[IPT], uint32_t* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 1; i < IPT; ++i) v[i] = max(v[i], v[i - 1]);
+  uint32_t tot = v[IPT - 1];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(FULL, tot, o);
+    if (lane >= o) tot = max(tot, n);
+  }
+  __syncthreads();
+  if (lane == 31) sm[w] = tot;
+  __syncthreads();
+  uint32_t pre = 0;  // exclusive prefix over previous warps
+  for (int k = 0; k < w; ++k) pre = max(pre, sm[k]);
+  uint32_t prev = __shfl_up_sync(FULL, tot, 1);
+  if (lane == 0) prev = 0;
+  pre = max(pre, prev);
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) v[i] = max(v[i], pre);
+}
+
+template <int NT, int IPT>
+__device__ __forceinline__ void block_scan_min_rev(uint32_t (&v)[IPT], uint32_t* sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = IPT - 2; i >= 0; --i) v[i] = min(v[i], v[i + 1]);
+  uint32_t tot = v[0];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_down_sync(FULL, tot, o);
+    if (lane + o < 32) tot = min(tot, n);
+  }
+  __syncthreads();
+  if (lane == 0) sm[w] = tot;
+  __syncthreads();
+  uint32_t pre = 0xffffffffu;
+  for (int k = w + 1; k < NT / 32; ++k) pre = min(pre, sm[k]);
+  uint32_t nxt = __shfl_down_sync(FULL, tot, 1);
+  if (lane == 31) nxt = 0xffffffffu;
+  pre = min(pre, nxt);
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) v[i] = min(v[i], pre);
+}
+
+}  // namespace b200ref

@@ -1,0 +1,312 @@
+// Tie-averaged pooled ranks -> normal scores, for the raw draws and for the folded
+// draws, written back to the draws' original [C][N] positions.
+//
+//   k_param_prep      pooled median (statistics.median, diagnostics.py:97), the split
+//                     point of the folded order, numpy-linear quantiles
+//                     (backends_numpy.py:44) and their order statistics.
+//   k_rank            one tile of the sorted keys: tie runs by equality
+//                     (diagnostics.py:113-122), k = i + j, z = T[k], scatter.
+//   k_merge_partition merge-path split points of the folded order.
+//   k_fold            folded values |v - med| (diagnostics.py:98) are monotone on each
+//                     side of the median, so their ascending order is the MERGE of the
+//                     reversed left part and the right part of the already sorted
+//                     sequence -- no second sort.  Same tie/z/scatter step.
+#pragma once
+#include "as241.cuh"
+#include "common.cuh"
+
+namespace b200ref {
+
+constexpr int RANK_NT = 256;
+constexpr int RANK_IPT = 8;
+constexpr int RANK_TILE = RANK_NT * RANK_IPT;
+
+struct RankBufs {
+  const uint64_t* key[2];  // sorted keys are in key[sel[p]]
+  const uint32_t* idx[2];
+  const int* sel;
+  const double* sum;   // [PB] sum of draws
+  double* med;         // [PB]
+  uint32_t* m0;        // [PB] number of draws strictly below the median
+  uint32_t* apos;      // [PB][ntiles+1] merge-path split (count taken from the left part)
+  double* sqpart;      // [PB][ntiles] partial sums of (v - mean)^2
+  const double* ztab;  // [2M]
+};
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t lo, uint32_t hi, uint64_t v) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t* a, uint32_t lo, uint32_t hi, uint64_t v) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// numpy's linear quantile on a sorted sequence: virtual index (n-1)*q,
+// _lerp(a, b, g) = a + (b-a)*g if g < 0.5 else b - (b-a)*(1-g); no FMA contraction.
+__device__ __forceinline__ double quantile_lerp(const uint64_t* keys, uint32_t M, double q, double* os) {
+  const double vi = __dmul_rn((double)(M - 1), q);
+  double fl = floor(vi);
+  uint32_t lo = (uint32_t)fl;
+  if (lo > M - 1) lo = M - 1;
+  const uint32_t hi = (lo + 1 < M) ? lo + 1 : M - 1;
+  const double g = __dsub_rn(vi, fl);
+  const double a = key2dbl(keys[lo]);
+  const double b = key2dbl(keys[hi]);
+  if (os) { os[0] = a; os[1] = b; }
+  const double diff = __dsub_rn(b, a);
+  return (g < 0.5) ? __dadd_rn(a, __dmul_rn(diff, g)) : __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, g)));
+}
+
+struct PrepOut {
+  double* quant;   // [P][nq] or null
+  double* ostats;  // [P][nq][2] or null
+  double* median;  // [P] or null
+  double* mean;    // [P] or null
+};
+
+struct QuantArgs {
+  double q[8];
+  int nq;
+};
+
+__global__ void k_param_prep(RankBufs b, uint32_t M, int PB, QuantArgs qa, PrepOut o) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= PB) return;
+  const uint64_t* keys = b.key[b.sel[p]] + (size_t)p * M;
+  double med;
+  if (M & 1u) med = key2dbl(keys[M / 2]);
+  else med = __dmul_rn(__dadd_rn(key2dbl(keys[M / 2 - 1]), key2dbl(keys[M / 2])), 0.5);
+  b.med[p] = med;
+  b.m0[p] = lower_bound_u64(keys, 0, M, dbl2key(med));
+  if (o.median) o.median[p] = med;
+  if (o.mean) o.mean[p] = b.sum[p] / (double)M;
+  for (int i = 0; i < qa.nq; ++i) {
+    double os[2];
+    const double v = quantile_lerp(keys, M, qa.q[i], os);
+    if (o.quant) o.quant[(size_t)p * qa.nq + i] = v;
+    if (o.ostats) {
+      o.ostats[((size_t)p * qa.nq + i) * 2 + 0] = os[0];
+      o.ostats[((size_t)p * qa.nq + i) * 2 + 1] = os[1];
+    }
+  }
+}
+
+// sv[1 + e] = element e of the tile (ascending), sv[0] / sv[n + 1] = neighbours outside
+// the tile (valid iff has_prev / has_next).  Returns k = i + j per item, where
+// [i, j) is the element's tie run in the whole sequence.  ext_i / ext_j are the run
+// bounds of runs that cross the tile's first / last element (only read if needed).
+template <int NT, int IPT>
+__device__ __forceinline__ void tie_codes(const uint64_t* sv, uint32_t n, uint32_t gbase, bool has_prev,
+                                          bool has_next, const uint32_t* ext, uint32_t* scan_sm,
+                                          uint32_t (&kout)[IPT]) {
+  uint32_t hi[IPT], tj[IPT];
+#pragma unroll
+  for (int it = 0; it < IPT; ++it) {
+    const uint32_t e = threadIdx.x * IPT + it;
+    hi[it] = 0;
+    tj[it] = 0xffffffffu;
+    if (e < n) {
+      const uint64_t cur = sv[e + 1];
+      const bool head = (e == 0) ? !(has_prev && sv[0] == cur) : (sv[e] != cur);
+      const bool tail = (e == n - 1) ? !(has_next && sv[n + 1] == cur) : (sv[e + 2] != cur);
+      if (head) hi[it] = gbase + e + 1;
+      if (tail) tj[it] = gbase + e + 1;
+    }
+  }
+  block_scan_max_fwd<NT, IPT>(hi, scan_sm);
+  block_scan_min_rev<NT, IPT>(tj, scan_sm);
+#pragma unroll
+  for (int it = 0; it < IPT; ++it) {
+    const uint32_t i = hi[it] ? hi[it] - 1 : ext[0];
+    const uint32_t j = (tj[it] != 0xffffffffu) ? tj[it] : ext[1];
+    kout[it] = i + j;
+  }
+}
+
+struct ScatterOut {
+  double* z;     // [PB][M] normal scores in original positions (or null)
+  double* rank;  // [PB][M] average ranks in original positions (or null)
+};
+
+__global__ void __launch_bounds__(RANK_NT) k_rank(RankBufs b, uint32_t M, uint32_t ntiles, ScatterOut o) {
+  __shared__ uint64_t sv[RANK_TILE + 2];
+  __shared__ uint32_t ext[2];
+  __shared__ uint32_t scan_sm[RANK_NT / 32];
+  __shared__ double red[33];
+  const int p = blockIdx.y;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t gbase = tile * RANK_TILE;
+  const uint32_t n = min((uint32_t)RANK_TILE, M - gbase);
+  const int s = b.sel[p];
+  const uint64_t* keys = b.key[s] + (size_t)p * M;
+  const uint32_t* idx = b.idx[s] + (size_t)p * M;
+  const bool has_prev = gbase > 0, has_next = gbase + n < M;
+
+  for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) sv[e + 1] = keys[gbase + e];
+  if (threadIdx.x == 0) sv[0] = has_prev ? keys[gbase - 1] : 0;
+  if (threadIdx.x == 32) sv[n + 1] = has_next ? keys[gbase + n] : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[1]) ? lower_bound_u64(keys, 0, gbase, sv[1]) : 0;
+  if (threadIdx.x == 32)
+    ext[1] = (has_next && sv[n + 1] == sv[n]) ? upper_bound_u64(keys, gbase + n, M, sv[n]) : 0;
+  __syncthreads();
+
+  uint32_t k[RANK_IPT];
+  tie_codes<RANK_NT, RANK_IPT>(sv, n, gbase, has_prev, has_next, ext, scan_sm, k);
+
+  const double mean = b.sum[p] / (double)M;
+  double sq = 0.0;
+  const size_t pbase = (size_t)p * M;
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    const uint32_t e = threadIdx.x * RANK_IPT + it;
+    if (e < n) {
+      const double d = key2dbl(sv[e + 1]) - mean;
+      sq += d * d;
+      const uint32_t pos = idx[gbase + e];
+      if (o.z) o.z[pbase + pos] = b.ztab[k[it]];
+      if (o.rank) o.rank[pbase + pos] = (double)(k[it] + 1u) * 0.5;
+    }
+  }
+  sq = block_sum<RANK_NT>(sq, red);
+  if (threadIdx.x == 0) b.sqpart[(size_t)p * ntiles + tile] = sq;
+}
+
+// Folded views of the sorted sequence s[0..M): left part reversed and right part,
+// both ascending in |v - med|.
+struct FoldView {
+  const uint64_t* keys;
+  uint32_t m0, M;
+  double med;
+  __device__ __forceinline__ uint64_t fbits(uint32_t t) const {
+    return (uint64_t)__double_as_longlong(fabs(__dsub_rn(key2dbl(keys[t]), med)));
+  }
+  __device__ __forceinline__ uint32_t nL() const { return m0; }
+  __device__ __forceinline__ uint32_t nR() const { return M - m0; }
+  __device__ __forceinline__ uint64_t L(uint32_t a) const { return fbits(m0 - 1 - a); }
+  __device__ __forceinline__ uint64_t R(uint32_t c) const { return fbits(m0 + c); }
+  // merge-path: number of left-part elements among the first o outputs (left first on ties)
+  __device__ uint32_t split(uint32_t o) const {
+    uint32_t lo = (o > nR()) ? o - nR() : 0, hi = min(o, nL());
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (L(mid) <= R(o - 1 - mid)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+  __device__ uint32_t count_less(uint64_t d) const {  // elements of both parts with value < d
+    uint32_t lo = 0, hi = nL();
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (L(mid) < d) lo = mid + 1; else hi = mid; }
+    uint32_t c = lo;
+    lo = 0; hi = nR();
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (R(mid) < d) lo = mid + 1; else hi = mid; }
+    return c + lo;
+  }
+  __device__ uint32_t count_leq(uint64_t d) const {
+    uint32_t lo = 0, hi = nL();
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (L(mid) <= d) lo = mid + 1; else hi = mid; }
+    uint32_t c = lo;
+    lo = 0; hi = nR();
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (R(mid) <= d) lo = mid + 1; else hi = mid; }
+    return c + lo;
+  }
+};
+
+__global__ void k_merge_partition(RankBufs b, uint32_t M, uint32_t ntiles, int PB) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (q > ntiles || p >= PB) return;
+  FoldView f{b.key[b.sel[p]] + (size_t)p * M, b.m0[p], M, b.med[p]};
+  const uint32_t o = min(q * (uint32_t)RANK_TILE, M);
+  b.apos[(size_t)p * (ntiles + 1) + q] = f.split(o);
+}
+
+__global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, ScatterOut o) {
+  __shared__ uint64_t sd[RANK_TILE];      // left window then right window (folded bits)
+  __shared__ uint32_t si[RANK_TILE];      // their original positions
+  __shared__ uint64_t sv[RANK_TILE + 2];  // merged
+  __shared__ uint32_t ext[2];
+  __shared__ uint32_t scan_sm[RANK_NT / 32];
+  const int p = blockIdx.y;
+  const uint32_t tile = blockIdx.x;
+  const int s = b.sel[p];
+  const uint32_t* idx = b.idx[s] + (size_t)p * M;
+  FoldView f{b.key[s] + (size_t)p * M, b.m0[p], M, b.med[p]};
+  const uint32_t gbase = tile * RANK_TILE;
+  const uint32_t n = min((uint32_t)RANK_TILE, M - gbase);
+  const uint32_t a0 = b.apos[(size_t)p * (ntiles + 1) + tile];
+  const uint32_t a1 = b.apos[(size_t)p * (ntiles + 1) + tile + 1];
+  const uint32_t c0 = gbase - a0, c1 = gbase + n - a1;
+  const uint32_t nl = a1 - a0, nr = c1 - c0;
+  const bool has_prev = gbase > 0, has_next = gbase + n < M;
+
+  for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) {
+    const uint32_t t = (e < nl) ? (f.m0 - 1 - (a0 + e)) : (f.m0 + c0 + (e - nl));
+    sd[e] = f.fbits(t);
+    si[e] = idx[t];
+  }
+  if (threadIdx.x == 0) {
+    // merged element just before the tile: the larger of the two preceding heads
+    uint64_t pv = 0;
+    if (a0 > 0) pv = f.L(a0 - 1);
+    if (c0 > 0) pv = max(pv, f.R(c0 - 1));
+    sv[0] = pv;
+  }
+  if (threadIdx.x == 32) {
+    uint64_t nv = ~0ull;
+    if (a1 < f.nL()) nv = f.L(a1);
+    if (c1 < f.nR()) nv = min(nv, f.R(c1));
+    sv[n + 1] = nv;
+  }
+  __syncthreads();
+
+  // per-thread merge path inside the tile
+  uint32_t midx[RANK_IPT];
+  {
+    const uint32_t od = min((uint32_t)threadIdx.x * RANK_IPT, n);
+    uint32_t lo = (od > nr) ? od - nr : 0, hi = min(od, nl);
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (sd[mid] <= sd[nl + od - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    uint32_t la = lo, lc = od - lo;
+#pragma unroll
+    for (int it = 0; it < RANK_IPT; ++it) {
+      const uint32_t e = od + it;
+      midx[it] = 0;
+      if (e < n) {
+        const bool takeL = (la < nl) && (lc >= nr || sd[la] <= sd[nl + lc]);
+        const uint32_t src = takeL ? la : nl + lc;
+        sv[e + 1] = sd[src];
+        midx[it] = si[src];
+        la += takeL ? 1u : 0u;
+        lc += takeL ? 0u : 1u;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[1]) ? f.count_less(sv[1]) : 0;
+  if (threadIdx.x == 32) ext[1] = (has_next && sv[n + 1] == sv[n]) ? f.count_leq(sv[n]) : 0;
+  __syncthreads();
+
+  uint32_t k[RANK_IPT];
+  tie_codes<RANK_NT, RANK_IPT>(sv, n, gbase, has_prev, has_next, ext, scan_sm, k);
+  const size_t pbase = (size_t)p * M;
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    const uint32_t e = threadIdx.x * RANK_IPT + it;
+    if (e < n) {
+      if (o.z) o.z[pbase + midx[it]] = b.ztab[k[it]];
+      if (o.rank) o.rank[pbase + midx[it]] = (double)(k[it] + 1u) * 0.5;
+    }
+  }
+}
+
+}  // namespace b200ref

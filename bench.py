@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the diagnostics + compare pass (BASELINE.json metric: draw*params/s).
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the reference algorithm on host cores
+
+A step = one full pass over the workload's parameter shard: sort -> tie ranks -> normal
+scores (raw + folded) -> split R-hat, bulk/tail ESS, mean/std/quantiles of the candidate
+draws; mean/std/quantiles of the reference draws; compare verdicts (tol 0.15); for N > 1
+the NCCL gather of the [P, 16] summaries and the AND of the verdicts.
+
+Workloads (per GPU, weak scaling: parameters are sharded by column):
+  c2      1000 params x 16 chains x 10000 draws + 10x1000 reference draws  (BASELINE configs[1])
+  c5tile  12500 params x 64 chains x 4096 draws (1/8 of configs[4]; 8 GPUs = the full config)
+  tiny    64 x 4 x 1000 (self-test)
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "mcmc-db_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    "c2": dict(P=1000, C=16, N=10000, RC=10, RN=1000,
+               name="c2: 1000 params x 16 chains x 10000 draws vs 10x1000 reference draws, per GPU"),
+    "c5tile": dict(P=12500, C=64, N=4096, RC=10, RN=1000,
+                   name="c5 shard: 12500 params x 64 chains x 4096 draws per GPU (8 GPUs = 100k params)"),
+    "tiny": dict(P=64, C=4, N=1000, RC=10, RN=100, name="tiny self-test 64 x 4 x 1000"),
+}
+METRIC = "diag+compare draw*params/s"
+UNIT = "draw*params/s"
+TOL = 0.15
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def algorithmic_bytes(w: dict) -> int:
+    """every fp64 draw read once + 16 output doubles per parameter."""
+    return 8 * w["P"] * (w["C"] * w["N"] + w["RC"] * w["RN"]) + 8 * 16 * w["P"]
+
+
+def gpu_arm(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mcmc_ref_b200 import _native, batch
+
+    w = WORKLOADS[args.workload]
+    P, C, N, MREF = w["P"], w["C"], w["N"], w["RC"] * w["RN"]
+    cand = batch.synth_fill(P, C, N, p0=rank * P, kind=0)
+    ref = batch.synth_fill(P, w["RC"], w["RN"], p0=rank * P, kind=1).reshape(P, MREF)
+    ws = batch.Workspace()
+    ws_cap = int(args.ws_gb * 2**30)
+    gathered = torch.empty((world * P, 16), dtype=torch.float64, device="cuda") if world > 1 else None
+    verdict = torch.ones(1, dtype=torch.int32, device="cuda")
+
+    def step():
+        summary, passed = batch.full_pass(cand, ref, tolerance=TOL, workspace=ws, ws_cap_bytes=ws_cap)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, summary)
+            verdict.fill_(1 if passed else 0)
+            dist.all_reduce(verdict, op=dist.ReduceOp.MIN)
+        return summary, passed
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        summary, passed = step()
+
+    # ---- timed region (device clock on the launching stream, max over ranks) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = _native.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        summary, passed = step()
+    e1.record()
+    barrier()
+    launches = _native.kernel_launches() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    nl = torch.tensor([launches], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(ms.item())
+    dp_per_step = world * P * C * N
+    value = dp_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- per-kernel device time over the same steps (events around every launch) ----
+    _native.profile(True)
+    _native.profile_read(reset=True)
+    barrier()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    prof = _native.profile_read(reset=True)
+    _native.profile(False)
+    peak, peak_src = measured_peak_gbs()
+    tot_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_n = prof[dom]
+    # algorithmic bytes of the launches of the dominant kernel: 8 B x draws each launch processes.
+    # All our heavy kernels are launched once per (batch, stage) over candidate and reference draws.
+    per_step_draw_bytes = 8 * P * (C * N + MREF)
+    launches_per_step_sets = {"k_radix_pass": 8}.get(dom, 1)
+    dom_alg_bytes = per_step_draw_bytes * launches_per_step_sets * args.steps
+    achieved = dom_alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "launches": dom_n, "avg_launch_ms": round(dom_ms / max(dom_n, 1), 4),
+                "share_of_kernel_time": round(dom_ms / tot_kernel_ms, 3),
+                "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}}
+    pass_gbs = algorithmic_bytes(w) * world * args.steps / (total_ms * 1e-3) / 1e9
+    pass_roofline = {"bound": "hbm", "achieved": round(pass_gbs, 1), "peak": peak * world, "unit": "GB/s",
+                     "frac": round(pass_gbs / (peak * world), 4),
+                     "note": "whole step: algorithmic bytes (each draw read once) / step time"}
+
+    # ---- end to end from HOST buffers through the public call (H2D + D2H inside the timed region) ----
+    cand_h = cand.cpu().pin_memory()
+    ref_h = ref.cpu().pin_memory()
+    sum_h = torch.empty((P, 16), dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        s, ok = batch.full_pass_host(cand_h, ref_h, tolerance=TOL, summary_host=sum_h, workspace=ws)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, s.cuda(non_blocking=True))
+            verdict.fill_(1 if ok else 0)
+            dist.all_reduce(verdict, op=dist.ReduceOp.MIN)
+        return s, ok
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s_host, ok_host = e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": dp_per_step * e2e_steps / float(e2e_s.item()), "unit": UNIT,
+           "h2d_bytes_per_step": 8 * P * (C * N + MREF) * world, "d2h_bytes_per_step": 8 * 16 * P * world,
+           "steps": e2e_steps, "call": "mcmc_ref_b200.batch.full_pass_host -> b200ref_full_pass_host_f64 (pinned host buffers)"}
+    same_bits = bool(np.array_equal(s_host.numpy(), summary.cpu().numpy(), equal_nan=True))
+
+    # ---- CPU baseline + parity gate on a bounded sample (rank 0, N = 1 only) ----
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.cpu_pool import OraclePool
+
+        pool = OraclePool()
+        ns = min(P, args.cpu_params_per_core * pool.cores)
+        idx = np.linspace(0, P - 1, ns).round().astype(int)
+        pool.stage(cand[idx].cpu().numpy(), ref[idx].cpu().numpy())
+        secs, want = pool.run(TOL)
+        pool.close()
+        cpu_baseline = {"value": ns * C * N / secs, "unit": UNIT, "cores": pool.cores, "kind": "port",
+                        "sample": f"{ns} of {P} params (evenly spaced) of the same device-generated workload, "
+                                  f"oracle/mcmc_oracle.py over a {pool.cores}-process pool, {secs:.1f} s"}
+        got = summary.cpu().numpy()[idx]
+        cols = batch.SUMMARY_COLUMNS
+        max_rel = 0.0
+        for k in ("rhat", "ess_bulk", "ess_tail", "mean", "std", "ref_mean", "ref_std"):
+            g, wv = got[:, cols.index(k)], want[k]
+            max_rel = max(max_rel, float(np.max(np.abs(g - wv) / np.maximum(np.abs(wv), 1e-300))))
+        exact = all(np.array_equal(got[:, cols.index(k)], want[k]) for k in
+                    ("q5", "q50", "q95", "ref_q5", "ref_q50", "ref_q95"))
+        flags = got[:, cols.index("flags")].astype(int)
+        verdicts = bool(np.array_equal((flags & 1) != 0, want["pass_mean"]) and
+                        np.array_equal((flags & 2) != 0, want["pass_std"]))
+        checks = bool(np.array_equal(got[:, 0] < 1.01, want["rhat"] < 1.01) and
+                      np.array_equal(got[:, 1] > 400, want["ess_bulk"] > 400))
+        parity = {"params_checked": int(ns), "max_rel_err_tolerance_class": max_rel, "quantiles_bit_exact": exact,
+                  "compare_verdicts_identical": verdicts, "check_verdicts_identical": checks,
+                  "ok": bool(max_rel < 1e-6 and exact and verdicts and checks)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "params_per_gpu": P, "chains": C, "draws": N, "ref_draws": MREF,
+                       "tolerance": TOL, "sharding": f"param columns x{world}",
+                       "l2": f"inputs larger than L2 ({algorithmic_bytes(w) / 1e9:.2f} GB read per step per GPU)",
+                       "compare_passed": bool(passed)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(nl.item()), "roofline": roofline,
+            "pass_roofline": pass_roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+            "e2e_bits_equal_device_path": same_bits,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args) -> None:
+    """The reference algorithm on the host cores (oracle port; the Python reference itself
+    cannot travel to the GPU box).  Rank 0 only; other ranks exit without work."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    from oracle.cpu_pool import OraclePool, host_workload
+
+    w = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
+    C, N, MREF = w["C"], w["N"], w["RC"] * w["RN"]
+    pool = OraclePool()
+    ns = min(w["P"], args.ref_params_per_core * pool.cores)
+    cand, ref = host_workload(ns, C, N, MREF)
+    pool.stage(cand, ref)
+    for _ in range(max(1, min(args.warmup, 3))):
+        pool.run(TOL)
+    t = 0.0
+    for _ in range(args.steps):
+        secs, out = pool.run(TOL)
+        t += secs
+    pool.close()
+    value = ns * C * N * args.steps / t
+    sample = (f"each step = {ns} of {w['P']} params of the workload (numpy-generated, same recipe), "
+              f"oracle port over a {pool.cores}-process pool")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "params_per_gpu": w["P"], "chains": C, "draws": N, "ref_draws": MREF,
+                   "tolerance": TOL, "sharding": "none (CPU)", "compare_passed": bool(out["passed"])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ws-gb", type=float, default=16.0, help="cap of the device workspace")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-params-per-core", type=int, default=24)
+    ap.add_argument("--ref-params-per-core", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,15 @@ const char* b200ref_last_error(void);
  * (monotone counter; bench.py reports the delta over its timed region). */
 uint64_t b200ref_kernel_launches(void);
 
+/* Per-kernel device timing for bench.py's roofline block.  While enabled, every
+ * kernel launch is bracketed by CUDA events on its launching stream.
+ * b200ref_profile_read synchronises the device, accumulates elapsed milliseconds and
+ * launch counts per kernel id into ms_out / launches_out (n entries each), optionally
+ * resets the accumulators, and returns the number of kernel ids. */
+int b200ref_profile(int enable);
+int b200ref_profile_read(double* ms_out, uint64_t* launches_out, int n, int reset);
+const char* b200ref_profile_name(int id);
+
 /* Workspace needed to process P parameters of C chains x N draws in one call
  * (the library loops over parameter batches internally if given less, down to
  * the size of one batch; see b200ref_workspace_min_bytes). */

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "as241.cuh"
 #include "chain.cuh"
@@ -40,7 +42,43 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                       \
   } while (0)
 
-#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+// ---- optional per-kernel timing (bench.py's roofline block): CUDA events recorded on the
+// launching stream around every kernel while enabled.
+enum KernelId { K_ZTABLE, K_HIST0, K_RADIX, K_PREP, K_RANK, K_MPART, K_FOLD, K_SUMSQ, K_CHAIN, K_FINALIZE,
+                K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_hist0", "k_radix_pass", "k_param_prep", "k_rank",
+                                           "k_merge_partition", "k_fold", "k_sumsq", "k_chain", "k_finalize",
+                                           "k_summary", "k_compare", "k_checks", "k_synth"};
+struct ProfRec { int id; cudaEvent_t a, b; };
+bool g_prof = false;
+std::vector<ProfRec> g_prof_recs;
+std::mutex g_prof_mu;
+double g_prof_ms[K_COUNT];
+uint64_t g_prof_n[K_COUNT];
+
+inline void prof_begin(int id, cudaStream_t st) {
+  if (!g_prof) return;
+  ProfRec r;
+  r.id = id;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back(r);
+}
+inline void prof_end(cudaStream_t st) {
+  if (!g_prof) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof_recs.back().b, st);
+}
+
+#define LAUNCH(id, st, ...)                                 \
+  do {                                                      \
+    prof_begin((id), (st));                                 \
+    __VA_ARGS__;                                            \
+    prof_end((st));                                         \
+    g_launches.fetch_add(1, std::memory_order_relaxed);     \
+  } while (0)
 
 constexpr size_t ALIGN = 256;
 inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
@@ -244,8 +282,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
 
   CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
   if (need_z || z_b || z_f) {
-    k_ztable<<<296, 256, 0, st>>>(ztab, (uint32_t)M);
-    LAUNCHED();
+    LAUNCH(K_ZTABLE, st, k_ztable<<<296, 256, 0, st>>>(ztab, (uint32_t)M));
   }
   QuantArgs qa;
   qa.nq = nq;
@@ -263,13 +300,10 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     sb.sel = (int*)(wb + L.sel);
     sb.sum = (double*)(wb + L.sum);
     sb.flag = flag;
-    k_hist0<<<PB, 1024, 0, st>>>(xb, (uint32_t)M, sb);
-    LAUNCHED();
-    k_radix_pass<true><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, 0, sb);
-    LAUNCHED();
+    LAUNCH(K_HIST0, st, k_hist0<<<PB, 1024, 0, st>>>(xb, (uint32_t)M, sb));
+    LAUNCH(K_RADIX, st, k_radix_pass<true><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, 0, sb));
     for (int pass = 1; pass < 8; ++pass) {
-      k_radix_pass<false><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, pass, sb);
-      LAUNCHED();
+      LAUNCH(K_RADIX, st, k_radix_pass<false><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, pass, sb));
     }
     RankBufs rb;
     rb.key[0] = sb.key[0]; rb.key[1] = sb.key[1];
@@ -286,8 +320,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     po.ostats = (out && out->order_stats) ? out->order_stats + (size_t)p0 * nq * 2 : nullptr;
     po.median = (out && out->median) ? out->median + p0 : nullptr;
     po.mean = (out && out->mean) ? out->mean + p0 : nullptr;
-    k_param_prep<<<(PB + 127) / 128, 128, 0, st>>>(rb, (uint32_t)M, PB, qa, po);
-    LAUNCHED();
+    LAUNCH(K_PREP, st, k_param_prep<<<(PB + 127) / 128, 128, 0, st>>>(rb, (uint32_t)M, PB, qa, po));
 
     const dim3 gt(L.ntiles, PB);
     const bool ranks = mode.diag || mode.want_ranks;
@@ -295,23 +328,18 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     double* zf = z_f ? z_f + (size_t)p0 * M : (need_z ? (double*)(wb + L.zf) : nullptr);
     if (ranks) {
       ScatterOut so{zb, rank_b ? rank_b + (size_t)p0 * M : nullptr};
-      k_rank<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, so);
-      LAUNCHED();
+      LAUNCH(K_RANK, st, k_rank<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, so));
       if (mode.diag || zf || rank_f) {
-        k_merge_partition<<<dim3((L.ntiles + 1 + 127) / 128, PB), 128, 0, st>>>(rb, (uint32_t)M, L.ntiles, PB);
-        LAUNCHED();
+        LAUNCH(K_MPART, st, k_merge_partition<<<dim3((L.ntiles + 1 + 127) / 128, PB), 128, 0, st>>>(rb, (uint32_t)M, L.ntiles, PB));
         ScatterOut sf{zf, rank_f ? rank_f + (size_t)p0 * M : nullptr};
-        k_fold<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, sf);
-        LAUNCHED();
+        LAUNCH(K_FOLD, st, k_fold<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, sf));
       }
     } else {
-      k_sumsq<<<gt, RANK_NT, 0, st>>>(xb, (uint32_t)M, L.ntiles, sb.sum, rb.sqpart);
-      LAUNCHED();
+      LAUNCH(K_SUMSQ, st, k_sumsq<<<gt, RANK_NT, 0, st>>>(xb, (uint32_t)M, L.ntiles, sb.sum, rb.sqpart));
     }
     ChainOut co{(double*)(wb + L.crhat), (double*)(wb + L.cess), (int64_t*)(wb + L.clag)};
     if (mode.diag) {
-      k_chain<<<dim3(PB, 2), CH_NT, chain_smem, st>>>(zb, zf, (uint32_t)C, (uint32_t)N, PB, co);
-      LAUNCHED();
+      LAUNCH(K_CHAIN, st, k_chain<<<dim3(PB, 2), CH_NT, chain_smem, st>>>(zb, zf, (uint32_t)C, (uint32_t)N, PB, co));
     }
     if (out) {
       FinalizeArgs fa;
@@ -332,8 +360,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
         fa.lag_bulk = out->lag_bulk ? out->lag_bulk + p0 : nullptr;
         fa.lag_tail = out->lag_tail ? out->lag_tail + p0 : nullptr;
       }
-      k_finalize<<<(PB + 127) / 128, 128, 0, st>>>(fa, (uint32_t)M, PB);
-      LAUNCHED();
+      LAUNCH(K_FINALIZE, st, k_finalize<<<(PB + 127) / 128, 128, 0, st>>>(fa, (uint32_t)M, PB));
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -363,6 +390,37 @@ size_t b200ref_workspace_min_bytes(int64_t C, int64_t N) {
   l.compute(1, C * N, true);
   return l.header + l.per_batch;
 }
+
+int b200ref_profile(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof = enable != 0;
+  return B200REF_OK;
+}
+
+int b200ref_profile_read(double* ms_out, uint64_t* launches_out, int n, int reset) {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      g_prof_ms[r.id] += ms;
+      g_prof_n[r.id] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+  for (int i = 0; i < n && i < K_COUNT; ++i) {
+    if (ms_out) ms_out[i] = g_prof_ms[i];
+    if (launches_out) launches_out[i] = g_prof_n[i];
+  }
+  if (reset) {
+    for (int i = 0; i < K_COUNT; ++i) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+  }
+  return K_COUNT;
+}
+
+const char* b200ref_profile_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : ""; }
 
 int b200ref_ranks_f64(const double* x, int64_t P, int64_t C, int64_t N, double* avg_rank, double* z,
                       double* avg_rank_folded, double* z_folded, void* ws, size_t ws_bytes, void* stream) {
@@ -401,8 +459,7 @@ int b200ref_compare_f64(const double* ref, const double* act, int64_t n, double 
   CUDA_TRY(cudaMallocAsync((void**)&nfail, sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(nfail, 0, sizeof(int), st));
   if (n > 0) {
-    k_compare<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ref, act, n, tol, rel_err, passed, nfail);
-    LAUNCHED();
+    LAUNCH(K_COMPARE, st, k_compare<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ref, act, n, tol, rel_err, passed, nfail));
   }
   int h = 0;
   CUDA_TRY(cudaMemcpyAsync(&h, nfail, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -425,8 +482,7 @@ int b200ref_checks_f64(const double* rhat, const double* essb, int64_t P, uint8_
   CUDA_TRY(cudaMallocAsync((void**)&viol, 2 * sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(viol, 0, 2 * sizeof(int), st));
   if (P > 0) {
-    k_checks<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(rhat, essb, P, viol);
-    LAUNCHED();
+    LAUNCH(K_CHECKS, st, k_checks<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(rhat, essb, P, viol));
   }
   int h[2] = {0, 0};
   CUDA_TRY(cudaMemcpyAsync(h, viol, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -466,9 +522,8 @@ int b200ref_full_pass_f64(const double* cand, int64_t P, int64_t C, int64_t N, c
   rc = run(ref, P, 1, Mref, qs, 3, &orf, nullptr, nullptr, nullptr, nullptr, Mode{false, false}, ws, body, st);
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(nfail, 0, sizeof(int), st));
-  k_summary<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(rhat, essb, esst, mean, sd, q, rmean, rsd, rq, tol, P,
-                                                         summary, nfail);
-  LAUNCHED();
+  LAUNCH(K_SUMMARY, st, k_summary<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(rhat, essb, esst, mean, sd, q, rmean, rsd, rq, tol, P,
+                                                         summary, nfail));
   int h = 0;
   CUDA_TRY(cudaMemcpyAsync(&h, nfail, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -563,8 +618,7 @@ int b200ref_synth_fill_f64(double* x, int64_t p0, int64_t P, int64_t C, int64_t 
   const int64_t nchains = P * C;
   const int warps_per_block = 8;
   const unsigned blocks = (unsigned)((nchains + warps_per_block - 1) / warps_per_block);
-  k_synth<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(x, p0, P, C, N, seed, kind);
-  LAUNCHED();
+  LAUNCH(K_SYNTH, (cudaStream_t)stream, k_synth<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(x, p0, P, C, N, seed, kind));
   CUDA_TRY(cudaGetLastError());
   return B200REF_OK;
 }

@@ -18,6 +18,7 @@ MAX_QUANTILES = 8
 
 EXPORTS = (
     "b200ref_version", "b200ref_last_error", "b200ref_kernel_launches",
+    "b200ref_profile", "b200ref_profile_read", "b200ref_profile_name",
     "b200ref_workspace_bytes", "b200ref_workspace_min_bytes",
     "b200ref_ranks_f64", "b200ref_diagnostics_f64", "b200ref_stats_f64",
     "b200ref_compare_f64", "b200ref_checks_f64",
@@ -60,6 +61,10 @@ def load() -> C.CDLL:
     lib.b200ref_version.restype = C.c_int
     lib.b200ref_last_error.restype = C.c_char_p
     lib.b200ref_kernel_launches.restype = u64
+    lib.b200ref_profile.argtypes = [C.c_int]
+    lib.b200ref_profile_read.argtypes = [C.POINTER(dbl), C.POINTER(u64), C.c_int, C.c_int]
+    lib.b200ref_profile_name.restype = C.c_char_p
+    lib.b200ref_profile_name.argtypes = [C.c_int]
     lib.b200ref_workspace_bytes.restype = sz
     lib.b200ref_workspace_bytes.argtypes = [i64, i64, i64]
     lib.b200ref_workspace_min_bytes.restype = sz
@@ -94,3 +99,17 @@ def check(rc: int) -> None:
 
 def kernel_launches() -> int:
     return int(load().b200ref_kernel_launches())
+
+
+def profile(enable: bool) -> None:
+    load().b200ref_profile(1 if enable else 0)
+
+
+def profile_read(reset: bool = True) -> dict[str, tuple[float, int]]:
+    """{kernel name: (total ms, launches)} accumulated while profiling was enabled."""
+    lib = load()
+    n = lib.b200ref_profile_read(None, None, 0, 0)
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    lib.b200ref_profile_read(ms, cnt, n, 1 if reset else 0)
+    return {lib.b200ref_profile_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -170,9 +170,11 @@ def gpu_arm(args) -> None:
     dom_ms, dom_n = prof[dom]
     # algorithmic bytes of the launches of the dominant kernel: 8 B x draws each launch processes.
     # All our heavy kernels are launched once per (batch, stage) over candidate and reference draws.
-    per_step_draw_bytes = 8 * P * (C * N + MREF)
-    launches_per_step_sets = {"k_radix_pass": 8}.get(dom, 1)
-    dom_alg_bytes = per_step_draw_bytes * launches_per_step_sets * args.steps
+    # per step, a kernel is launched `sides` times over the candidate draws (8 B x P x C x N each)
+    # and, unless it is diagnostics-only, as often over the reference draws (8 B x P x MREF each).
+    per_side = {"k_radix_pass": 8}.get(dom, 1)
+    cand_only = dom in ("k_fold", "k_chain", "k_merge_partition")
+    dom_alg_bytes = args.steps * per_side * 8 * P * (C * N + (0 if cand_only else MREF))
     achieved = dom_alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"

@@ -1,0 +1,486 @@
+// Distribution sort of one parameter's pooled draws: the fast ordering path.
+//
+// Replaces the 8-pass LSD radix sort for the ordering step of _rank_normalize
+// (diagnostics.py:110) / np.quantile (backends_numpy.py:44) with ONE global
+// partition pass plus an on-chip finish:
+//
+//   k_sample     a strided sample (16 per coarse bucket) is sorted on-chip; every
+//                16th sample becomes a splitter, so coarse buckets hold ~M/NB1 draws
+//                for ANY continuous distribution (heavy tails, multi-modal, ...).
+//   k_bhist      reads the draws once: coarse-bucket counts per 4096-draw chunk,
+//                finiteness, and shifted power sums for mean / std.
+//   k_bscan      exclusive offsets per (chunk, bucket); mean / std; overflow flag.
+//   k_partition  reads the draws again, stages each chunk in shared memory in bucket
+//                order and writes (key64, position32) runs -- coalesced stores.
+//   k_finish     one CTA per coarse bucket (<= 2048 draws, all in shared memory):
+//                256 equal-width fine buckets, then each draw counts the smaller /
+//                equal keys of its fine bucket: exact rank, exact tie run [i, j),
+//                sorted position.  Writes the sorted (key, position, k = i + j).
+//
+// The bucket function only has to be MONOTONE for correctness (it is: floor of a
+// monotone fp expression, and "number of splitters <= x"); its uniformity only
+// affects speed.  A parameter whose data defeat it (a coarse bucket over capacity:
+// one value repeated > 2048 times, ...) is flagged and sorted by the LSD path instead.
+#pragma once
+#include "common.cuh"
+
+namespace b200ref {
+
+constexpr int NB1_MAX = 256;      // coarse buckets per parameter (power of two, <= 256)
+constexpr int NCELL = 1024;       // linear cells of the splitter lookup table
+constexpr int NFINE = 256;        // fine buckets per coarse bucket
+constexpr int CAP1 = 2048;        // draws a coarse bucket may hold (on-chip capacity of k_finish)
+constexpr int OVERSAMPLE = 16;    // samples per coarse bucket
+constexpr int CHUNK_P = 4096;     // draws per partition chunk
+constexpr int PART_NT = 256;
+constexpr int PART_IPT = CHUNK_P / PART_NT;
+constexpr int FIN_NT = 256;
+constexpr int FIN_IPT = CAP1 / FIN_NT;
+constexpr int BIG_FINE = 32;      // fine buckets larger than this are handled warp-cooperatively
+
+// Per-parameter bucket function, written by k_sample.
+struct BucketFn {
+  double lo, hi;      // sample min / max (cell range, and outer bounds for the fine level)
+  double cs;          // NCELL / (hi - lo), 0 if hi == lo
+  double c0;          // sample median: centre for the shifted power sums
+  double sp[NB1_MAX]; // sp[j], j = 0 .. nb1-2 : splitters (ascending); rest = +inf
+  uint16_t lut[NCELL + 2];  // lut[c] = number of splitters whose cell is < c
+  int nb1;
+  int pad;
+};
+
+__host__ __device__ inline int choose_nb1(int64_t M) {
+  int nb = 1;
+  while (nb < NB1_MAX && M > (int64_t)nb * 768) nb <<= 1;
+  return nb;
+}
+
+__device__ __forceinline__ int cell_of(double x, double lo, double cs) {
+  const double t = (x - lo) * cs;
+  int c = (t >= 0.0) ? ((t < (double)NCELL) ? (int)t : NCELL - 1) : 0;  // NaN (inf * 0) -> 0
+  return c;
+}
+
+// number of splitters <= x  (monotone in x)
+__device__ __forceinline__ int coarse_of(double x, double lo, double cs, const double* __restrict__ sp,
+                                         const uint16_t* __restrict__ lut) {
+  const int c = cell_of(x, lo, cs);
+  int a = lut[c];
+  const int e = lut[c + 1];
+  while (a < e && sp[a] <= x) ++a;
+  return a;
+}
+
+// fine bucket inside a coarse bucket with bounds [L, U): floor((x - L) * fs), clamped
+__device__ __forceinline__ int fine_of(double x, double L, double fs) {
+  const double t = (x - L) * fs;
+  return (t >= 0.0) ? ((t < (double)NFINE) ? (int)t : NFINE - 1) : 0;
+}
+
+struct BucketBufs {
+  BucketFn* fn;        // [PB]
+  uint32_t* cnt;       // [PB][nchunks][NB1_MAX]  per-chunk bucket counts -> exclusive offsets
+  uint32_t* boff;      // [PB][NB1_MAX + 1]       bucket start offsets in the sorted order
+  double* spart;       // [PB][nchunks][2]        shifted power sums per chunk
+  uint8_t* fallback;   // [PB] 1 = sort this parameter with the LSD path
+  int* flag;           // bit0 non-finite input
+  uint64_t* pkey;      // [PB][M] partitioned keys
+  uint32_t* pidx;      // [PB][M] partitioned positions
+  uint64_t* skey;      // [PB][M] sorted keys
+  uint32_t* sidx;      // [PB][M] sorted positions
+  uint32_t* kcode;     // [PB][M] k = i + j of each sorted element's tie run
+  int* sel;            // [PB] (LSD path compatibility: 1 = sorted data are in skey / sidx)
+  double* mean;        // [PB]
+  double* sd;          // [PB]
+};
+
+// ---------------------------------------------------------------- k_sample
+__global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, uint32_t M, BucketBufs b) {
+  __shared__ uint64_t s[NB1_MAX * OVERSAMPLE];
+  __shared__ int scell[NB1_MAX];
+  const int p = blockIdx.x;
+  const double* xp = x + (size_t)p * M;
+  BucketFn* fn = b.fn + p;
+  const int nb1 = choose_nb1(M);
+  const uint32_t S = min((uint32_t)(nb1 * OVERSAMPLE), M);  // samples actually taken
+  uint32_t S2 = 1;
+  while (S2 < S) S2 <<= 1;                                   // padded to a power of two
+  for (uint32_t j = threadIdx.x; j < S2; j += 512) {
+    uint64_t k = ~0ull;
+    if (j < S) {
+      const uint32_t t = (uint32_t)(((uint64_t)(2 * j + 1) * M) / (2 * S));
+      k = dbl2key(xp[t]);
+    }
+    s[j] = k;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= S2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = threadIdx.x; t < S2 / 2; t += 512) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        const uint32_t j = i + stride;
+        const bool up = ((i & size) == 0);
+        const uint64_t a = s[i], c = s[j];
+        if ((a > c) == up) { s[i] = c; s[j] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const double lo = key2dbl(s[0]), hi = key2dbl(s[S - 1]);
+  const double cs = (hi > lo) ? (double)NCELL / (hi - lo) : 0.0;
+  if (threadIdx.x == 0) {
+    fn->lo = lo; fn->hi = hi; fn->cs = isfinite(cs) ? cs : 0.0;
+    fn->c0 = key2dbl(s[S / 2]);
+    fn->nb1 = nb1;
+    b.fallback[p] = 0;
+    b.sel[p] = 1;
+  }
+  const double csf = isfinite(cs) ? cs : 0.0;
+  for (int j = threadIdx.x; j < NB1_MAX; j += 512) {
+    double v = __longlong_as_double(0x7ff0000000000000ll);
+    int c = NCELL;
+    if (j < nb1 - 1) {
+      v = key2dbl(s[(uint32_t)(((uint64_t)(j + 1) * S) / nb1)]);
+      c = cell_of(v, lo, csf);
+    }
+    fn->sp[j] = v;
+    scell[j] = c;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < NCELL + 2; c += 512) {
+    // number of splitters with cell < c  (scell ascending over j < nb1-1, NCELL beyond)
+    int a = 0, e = nb1 - 1;
+    while (a < e) { const int mid = (a + e) >> 1; if (scell[mid] < c) a = mid + 1; else e = mid; }
+    fn->lut[c] = (uint16_t)a;
+  }
+}
+
+// ---------------------------------------------------------------- k_bhist
+__global__ void __launch_bounds__(PART_NT) k_bhist(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
+                                                    BucketBufs b) {
+  __shared__ double sp[NB1_MAX];
+  __shared__ uint16_t lut[NCELL + 2];
+  __shared__ uint32_t cnt[NB1_MAX];
+  __shared__ double red[33 * 2];
+  const int p = blockIdx.y;
+  const uint32_t chunk = blockIdx.x;
+  const BucketFn* fn = b.fn + p;
+  const double* xp = x + (size_t)p * M;
+  for (int i = threadIdx.x; i < NB1_MAX; i += PART_NT) { sp[i] = fn->sp[i]; cnt[i] = 0; }
+  for (int i = threadIdx.x; i < NCELL + 2; i += PART_NT) lut[i] = fn->lut[i];
+  const double lo = fn->lo, cs = fn->cs, c0 = fn->c0;
+  __syncthreads();
+  const uint32_t base = chunk * CHUNK_P;
+  double s1 = 0.0, s2 = 0.0;
+  bool bad = false;
+#pragma unroll 4
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = base + it * PART_NT + threadIdx.x;
+    if (e < M) {
+      const double v = xp[e];
+      bad |= !is_finite_bits(v);
+      const double d = v - c0;
+      s1 += d;
+      s2 = fma(d, d, s2);
+      atomicAdd(&cnt[coarse_of(v, lo, cs, sp, lut)], 1u);
+    }
+  }
+  // deterministic block sums (fixed tree)
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red[w] = s1; red[33 + w] = s2; }
+  const int anybad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < PART_NT / 32; ++k) { a += red[k]; c += red[33 + k]; }
+    b.spart[((size_t)p * nchunks + chunk) * 2 + 0] = a;
+    b.spart[((size_t)p * nchunks + chunk) * 2 + 1] = c;
+    if (anybad) atomicOr(b.flag, 1);
+  }
+  uint32_t* out = b.cnt + ((size_t)p * nchunks + chunk) * NB1_MAX;
+  for (int i = threadIdx.x; i < NB1_MAX; i += PART_NT) out[i] = cnt[i];
+}
+
+// ---------------------------------------------------------------- k_bscan
+__global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks, BucketBufs b) {
+  __shared__ uint32_t wtot[NB1_MAX / 32];
+  __shared__ int over;
+  const int p = blockIdx.x;
+  const int t = threadIdx.x;
+  if (t == 0) over = 0;
+  __syncthreads();
+  uint32_t* cnt = b.cnt + (size_t)p * nchunks * NB1_MAX;
+  uint32_t run = 0;
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    const uint32_t v = cnt[(size_t)c * NB1_MAX + t];
+    cnt[(size_t)c * NB1_MAX + t] = run;
+    run += v;
+  }
+  if (run > (uint32_t)CAP1) over = 1;
+  // exclusive scan of the bucket totals over the 256 threads
+  const int lane = t & 31, w = t >> 5;
+  uint32_t incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint32_t pre = 0;
+  for (int k = 0; k < w; ++k) pre += wtot[k];
+  const uint32_t excl = pre + incl - run;
+  b.boff[(size_t)p * (NB1_MAX + 1) + t] = excl;
+  if (t == NB1_MAX - 1) b.boff[(size_t)p * (NB1_MAX + 1) + NB1_MAX] = excl + run;
+  for (uint32_t c = 0; c < nchunks; ++c) cnt[(size_t)c * NB1_MAX + t] += excl;
+  if (t == 0) {
+    // mean = c0 + S1/M ; var = (S2 - S1^2/M)/M  (sums about the sample median: no cancellation)
+    double s1 = 0.0, s2 = 0.0;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+      s1 += b.spart[((size_t)p * nchunks + c) * 2 + 0];
+      s2 += b.spart[((size_t)p * nchunks + c) * 2 + 1];
+    }
+    const double dm = (double)M;
+    const double m1 = s1 / dm;
+    b.mean[p] = b.fn[p].c0 + m1;
+    const double var = (s2 - s1 * m1) / dm;
+    b.sd[p] = sqrt(var > 0.0 ? var : 0.0);
+  }
+  __syncthreads();
+  if (t == 0 && over) b.fallback[p] = 1;
+}
+
+// ---------------------------------------------------------------- k_partition
+struct PartSmem {
+  uint64_t skey[CHUNK_P];
+  double sp[NB1_MAX];
+  uint32_t cnt[NB1_MAX];
+  uint32_t coff[NB1_MAX];
+  uint32_t goff[NB1_MAX];
+  uint32_t wtot[PART_NT / 32];
+  uint16_t lut[NCELL + 2];
+  uint16_t sloc[CHUNK_P];
+  uint8_t sbk[CHUNK_P];
+};
+
+__global__ void __launch_bounds__(PART_NT) k_partition(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
+                                                        BucketBufs b) {
+  extern __shared__ __align__(16) unsigned char part_smem_raw[];
+  PartSmem& sm = *reinterpret_cast<PartSmem*>(part_smem_raw);
+  double* sp = sm.sp;
+  uint16_t* lut = sm.lut;
+  uint32_t* cnt = sm.cnt;
+  uint32_t* coff = sm.coff;
+  uint32_t* goff = sm.goff;
+  uint32_t* wtot = sm.wtot;
+  uint64_t* skey = sm.skey;
+  uint16_t* sloc = sm.sloc;
+  uint8_t* sbk = sm.sbk;
+  const int p = blockIdx.y;
+  if (b.fallback[p]) return;
+  const uint32_t chunk = blockIdx.x;
+  const BucketFn* fn = b.fn + p;
+  const double* xp = x + (size_t)p * M;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < NB1_MAX; i += PART_NT) {
+    sp[i] = fn->sp[i];
+    cnt[i] = 0;
+    goff[i] = b.cnt[((size_t)p * nchunks + chunk) * NB1_MAX + i];
+  }
+  for (int i = tid; i < NCELL + 2; i += PART_NT) lut[i] = fn->lut[i];
+  const double lo = fn->lo, cs = fn->cs;
+  __syncthreads();
+  const uint32_t base = chunk * CHUNK_P;
+  const uint32_t n = min((uint32_t)CHUNK_P, M - base);
+  double v[PART_IPT];
+  uint32_t r[PART_IPT];
+  uint8_t bk[PART_IPT];
+#pragma unroll
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = it * PART_NT + tid;
+    v[it] = (e < n) ? xp[base + e] : 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = it * PART_NT + tid;
+    if (e < n) {
+      const int c = coarse_of(v[it], lo, cs, sp, lut);
+      bk[it] = (uint8_t)c;
+      r[it] = atomicAdd(&cnt[c], 1u);
+    }
+  }
+  __syncthreads();
+  {  // exclusive scan of cnt[256] with 256 threads
+    const int lane = tid & 31, w = tid >> 5;
+    const uint32_t c = cnt[tid];
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t nn = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += nn;
+    }
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (int k = 0; k < w; ++k) pre += wtot[k];
+    coff[tid] = pre + incl - c;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = it * PART_NT + tid;
+    if (e < n) {
+      const uint32_t slot = coff[bk[it]] + r[it];
+      skey[slot] = dbl2key(v[it]);
+      sloc[slot] = (uint16_t)e;
+      sbk[slot] = bk[it];
+    }
+  }
+  __syncthreads();
+  uint64_t* ok = b.pkey + (size_t)p * M;
+  uint32_t* oi = b.pidx + (size_t)p * M;
+  for (uint32_t s = tid; s < n; s += PART_NT) {
+    const int c = sbk[s];
+    const uint32_t pos = goff[c] + (s - coff[c]);
+    ok[pos] = skey[s];
+    oi[pos] = base + sloc[s];
+  }
+}
+
+// ---------------------------------------------------------------- k_finish
+struct FinishOut {
+  double* rank;   // optional [PB][M]: average ranks scattered to original positions (ranks API)
+};
+
+static_assert(FIN_NT == NFINE && NB1_MAX == 256 && PART_NT == NB1_MAX, "thread counts double as bin counts");
+
+__global__ void __launch_bounds__(FIN_NT) k_finish(uint32_t M, BucketBufs b, FinishOut fo) {
+  __shared__ uint64_t k2[CAP1];
+  __shared__ uint32_t i2[CAP1];
+  __shared__ uint32_t fh[NFINE];
+  __shared__ uint32_t foff[NFINE + 1];
+  __shared__ uint32_t wtot[FIN_NT / 32];
+  __shared__ uint32_t bigq[NFINE];
+  __shared__ uint32_t nbig;
+  const int p = blockIdx.y;
+  if (b.fallback[p]) return;
+  const int cb = blockIdx.x;
+  const BucketFn* fn = b.fn + p;
+  if (cb >= fn->nb1) return;
+  const uint32_t B0 = b.boff[(size_t)p * (NB1_MAX + 1) + cb];
+  const uint32_t n = b.boff[(size_t)p * (NB1_MAX + 1) + cb + 1] - B0;
+  if (n == 0) return;
+  const int tid = threadIdx.x;
+  // bounds of this coarse bucket for the fine level
+  const double L = (cb == 0) ? fn->lo : fn->sp[cb - 1];
+  const double U = (cb == fn->nb1 - 1) ? fn->hi : fn->sp[cb];
+  double fs = (U > L) ? (double)NFINE / (U - L) : 0.0;
+  if (!isfinite(fs)) fs = 0.0;
+  fh[tid] = 0;
+  if (tid == 0) nbig = 0;
+  __syncthreads();
+  const uint64_t* pk = b.pkey + (size_t)p * M + B0;
+  const uint32_t* pi = b.pidx + (size_t)p * M + B0;
+  uint64_t key[FIN_IPT];
+  uint32_t idx[FIN_IPT], r[FIN_IPT];
+  uint16_t f[FIN_IPT];
+#pragma unroll
+  for (int it = 0; it < FIN_IPT; ++it) {
+    const uint32_t e = it * FIN_NT + tid;
+    if (e < n) {
+      key[it] = pk[e];
+      idx[it] = pi[e];
+      f[it] = (uint16_t)fine_of(key2dbl(key[it]), L, fs);
+      r[it] = atomicAdd(&fh[f[it]], 1u);
+    }
+  }
+  __syncthreads();
+  {
+    const int lane = tid & 31, w = tid >> 5;
+    const uint32_t c = fh[tid];
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t nn = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += nn;
+    }
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (int k = 0; k < w; ++k) pre += wtot[k];
+    foff[tid] = pre + incl - c;
+    if (tid == NFINE - 1) foff[NFINE] = pre + incl;
+    if (c > (uint32_t)BIG_FINE) bigq[atomicAdd(&nbig, 1u)] = tid;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < FIN_IPT; ++it) {
+    const uint32_t e = it * FIN_NT + tid;
+    if (e < n) {
+      const uint32_t slot = foff[f[it]] + r[it];
+      k2[slot] = key[it];
+      i2[slot] = idx[it];
+    }
+  }
+  __syncthreads();
+  uint64_t* ok = b.skey + (size_t)p * M;
+  uint32_t* oi = b.sidx + (size_t)p * M;
+  uint32_t* oc = b.kcode + (size_t)p * M;
+  double* orank = fo.rank ? fo.rank + (size_t)p * M : nullptr;
+  // small fine buckets: one thread per slot scans its fine bucket
+  for (uint32_t s = tid; s < n; s += FIN_NT) {
+    const uint64_t k = k2[s];
+    const int fb = fine_of(key2dbl(k), L, fs);
+    const uint32_t a = foff[fb], e = foff[fb + 1];
+    if (e - a > (uint32_t)BIG_FINE) continue;
+    uint32_t less = 0, eq = 0, eqb = 0;
+    for (uint32_t t = a; t < e; ++t) {
+      const uint64_t kt = k2[t];
+      less += (kt < k);
+      eq += (kt == k);
+      eqb += (kt == k && t < s);
+    }
+    const uint32_t i = B0 + a + less;
+    const uint32_t pos = i + eqb;
+    ok[pos] = k;
+    oi[pos] = i2[s];
+    oc[pos] = 2 * i + eq;  // i + j with j = i + eq
+    if (orank) orank[i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
+  }
+  // big fine buckets (heavy ties or a density spike): one warp per bucket
+  const uint32_t nb = nbig;
+  const int lane = tid & 31, w = tid >> 5;
+  for (uint32_t q = w; q < nb; q += FIN_NT / 32) {
+    const int fb = bigq[q];
+    const uint32_t a = foff[fb], e = foff[fb + 1];
+    uint64_t mn = ~0ull, mx = 0;
+    for (uint32_t t = a + lane; t < e; t += 32) { const uint64_t kt = k2[t]; mn = min(mn, kt); mx = max(mx, kt); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+      mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+    }
+    for (uint32_t s = a + lane; s < e; s += 32) {
+      const uint64_t k = k2[s];
+      uint32_t less = 0, eq = e - a, eqb = s - a;
+      if (mn != mx) {
+        less = 0; eq = 0; eqb = 0;
+        for (uint32_t t = a; t < e; ++t) {
+          const uint64_t kt = k2[t];
+          less += (kt < k);
+          eq += (kt == k);
+          eqb += (kt == k && t < s);
+        }
+      }
+      const uint32_t i = B0 + a + less;
+      const uint32_t pos = i + eqb;
+      ok[pos] = k;
+      oi[pos] = i2[s];
+      oc[pos] = 2 * i + eq;
+      if (orank) orank[i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
+    }
+  }
+}
+
+}  // namespace b200ref

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "as241.cuh"
+#include "bucket.cuh"
 #include "chain.cuh"
 #include "common.cuh"
 #include "rank.cuh"
@@ -44,10 +45,11 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- optional per-kernel timing (bench.py's roofline block): CUDA events recorded on the
 // launching stream around every kernel while enabled.
-enum KernelId { K_ZTABLE, K_HIST0, K_RADIX, K_PREP, K_RANK, K_MPART, K_FOLD, K_SUMSQ, K_CHAIN, K_FINALIZE,
-                K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_COUNT };
-const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_hist0", "k_radix_pass", "k_param_prep", "k_rank",
-                                           "k_merge_partition", "k_fold", "k_sumsq", "k_chain", "k_finalize",
+enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_HIST0, K_RADIX, K_RANKC, K_PREP,
+                K_MPART, K_FOLD, K_CHAIN, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_sample", "k_bhist", "k_bscan", "k_partition", "k_finish",
+                                           "k_hist0", "k_radix_pass", "k_rank_codes", "k_param_prep",
+                                           "k_merge_partition", "k_fold", "k_chain", "k_finalize",
                                            "k_summary", "k_compare", "k_checks", "k_synth"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 bool g_prof = false;
@@ -86,29 +88,37 @@ inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 // Workspace carve-up for one batch of PB parameters with M pooled draws each.
 struct Layout {
   size_t ztab, flag, header;  // shared part
-  size_t key0, key1, idx0, idx1, zb, zf, hist, sel, sum, med, m0, apos, sqpart, crhat, cess, clag, per_batch;
-  uint32_t ntiles;
+  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, spart, fallback, hist, sel, sum, mean, sd, med, m0, apos,
+      crhat, cess, clag, per_batch;
+  uint32_t ntiles, nchunks;
   void compute(int64_t PB, int64_t M, bool diag) {
     ntiles = (uint32_t)((M + RANK_TILE - 1) / RANK_TILE);
+    nchunks = (uint32_t)((M + CHUNK_P - 1) / CHUNK_P);
     size_t o = 0;
     ztab = o; o += up(2 * (size_t)M * sizeof(double));
     flag = o; o += up(sizeof(int));
     header = o;
     size_t b = 0;
     const size_t n = (size_t)PB * (size_t)M;
-    key0 = b; b += up(n * 8);
-    key1 = b; b += up(n * 8);
-    idx0 = b; b += up(n * 4);
-    idx1 = b; b += up(n * 4);
-    zb = b; b += diag ? up(n * 8) : 0;
-    zf = b; b += diag ? up(n * 8) : 0;
+    pkey = b; b += up(n * 8);
+    skey = b; b += up(n * 8);
+    pidx = b; b += up(n * 4);
+    sidx = b; b += up(n * 4);
+    kcode = b; b += up(n * 4);
+    zz = b; b += diag ? up(n * 16) : 0;
+    fn = b; b += up((size_t)PB * sizeof(BucketFn));
+    cnt = b; b += up((size_t)PB * nchunks * NB1_MAX * 4);
+    boff = b; b += up((size_t)PB * (NB1_MAX + 1) * 4);
+    spart = b; b += up((size_t)PB * nchunks * 2 * 8);
+    fallback = b; b += up((size_t)PB);
     hist = b; b += up((size_t)PB * 8 * 256 * 4);
     sel = b; b += up((size_t)PB * 4);
     sum = b; b += up((size_t)PB * 8);
+    mean = b; b += up((size_t)PB * 8);
+    sd = b; b += up((size_t)PB * 8);
     med = b; b += up((size_t)PB * 8);
     m0 = b; b += up((size_t)PB * 4);
     apos = b; b += up((size_t)PB * (ntiles + 1) * 4);
-    sqpart = b; b += up((size_t)PB * ntiles * 8);
     crhat = b; b += up((size_t)PB * 2 * 8);
     cess = b; b += up((size_t)PB * 2 * 8);
     clag = b; b += up((size_t)PB * 2 * 8);
@@ -132,30 +142,14 @@ constexpr int64_t BATCH_CAP = 4096;
 
 // ---- small kernels used only by the orchestration ----
 
-__global__ void k_sumsq(const double* __restrict__ x, uint32_t M, uint32_t ntiles, const double* __restrict__ sum,
-                        double* __restrict__ sqpart) {
-  __shared__ double red[33];
-  const int p = blockIdx.y;
-  const uint32_t base = blockIdx.x * RANK_TILE;
-  const double mean = sum[p] / (double)M;
-  const double* xp = x + (size_t)p * M;
-  double sq = 0.0;
-  for (uint32_t e = base + threadIdx.x; e < min(base + (uint32_t)RANK_TILE, M); e += RANK_NT) {
-    const double d = xp[e] - mean;
-    sq += d * d;
-  }
-  sq = block_sum<RANK_NT>(sq, red);
-  if (threadIdx.x == 0) sqpart[(size_t)p * ntiles + blockIdx.x] = sq;
-}
-
 struct FinalizeArgs {
-  const double* sum;      // [PB]
-  const double* sqpart;   // [PB][ntiles]
+  const double* mean;     // [PB]
+  const double* sd;       // [PB]
   const double* crhat;    // [2][PB] or null
   const double* cess;     // [2][PB]
   const long long* clag;  // [2][PB]
-  uint32_t ntiles;
-  double* std_out;        // [PB] or null (already offset to this batch)
+  double* mean_out;       // [PB] or null (already offset to this batch)
+  double* std_out;
   double* rhat;           // or null
   double* rhat_bulk;
   double* rhat_tail;
@@ -168,11 +162,8 @@ struct FinalizeArgs {
 __global__ void k_finalize(FinalizeArgs a, uint32_t M, int PB) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= PB) return;
-  if (a.std_out) {
-    double s = 0.0;
-    for (uint32_t t = 0; t < a.ntiles; ++t) s += a.sqpart[(size_t)p * a.ntiles + t];
-    a.std_out[p] = sqrt(s / (double)M);
-  }
+  if (a.mean_out) a.mean_out[p] = a.mean[p];
+  if (a.std_out) a.std_out[p] = a.sd[p];
   if (a.crhat) {
     const double rb = a.crhat[p], rt = a.crhat[(size_t)PB + p];
     // Python max(rb, rt): keeps rb unless rt > rb (diagnostics.py:40)
@@ -271,82 +262,109 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     CUDA_TRY(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));
   }
   const bool need_z = mode.diag;
-  const int64_t PBmax = fit_batch(P, M, need_z && !z_b, ws_bytes, BATCH_CAP);
+  const bool ws_zz = mode.diag;  // interleaved {z_bulk, z_folded} scratch for k_chain
+  const int64_t PBmax = fit_batch(P, M, ws_zz, ws_bytes, BATCH_CAP);
   if (PBmax < 1) return fail(B200REF_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one parameter", ws_bytes);
   Layout L;
-  L.compute(PBmax, M, need_z && !z_b);
+  L.compute(PBmax, M, ws_zz);
   char* w = (char*)ws;
   double* ztab = (double*)(w + L.ztab);
   int* flag = (int*)(w + L.flag);
   char* wb = w + L.header;
+  static bool part_attr = false;
+  if (!part_attr) {
+    CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    part_attr = true;
+  }
 
   CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  if (need_z || z_b || z_f) {
-    LAUNCH(K_ZTABLE, st, k_ztable<<<296, 256, 0, st>>>(ztab, (uint32_t)M));
-  }
+  const bool want_scores = need_z || z_b || z_f || rank_f;
+  if (want_scores) LAUNCH(K_ZTABLE, st, k_ztable<<<296, 256, 0, st>>>(ztab, (uint32_t)M));
   QuantArgs qa;
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q_host[i];
+  const int nb1 = choose_nb1(M);
 
   for (int64_t p0 = 0; p0 < P; p0 += PBmax) {
     const int PB = (int)std::min<int64_t>(PBmax, P - p0);
     const double* xb = x + (size_t)p0 * M;
+    BucketBufs bb;
+    bb.fn = (BucketFn*)(wb + L.fn);
+    bb.cnt = (uint32_t*)(wb + L.cnt);
+    bb.boff = (uint32_t*)(wb + L.boff);
+    bb.spart = (double*)(wb + L.spart);
+    bb.fallback = (uint8_t*)(wb + L.fallback);
+    bb.flag = flag;
+    bb.pkey = (uint64_t*)(wb + L.pkey);
+    bb.pidx = (uint32_t*)(wb + L.pidx);
+    bb.skey = (uint64_t*)(wb + L.skey);
+    bb.sidx = (uint32_t*)(wb + L.sidx);
+    bb.kcode = (uint32_t*)(wb + L.kcode);
+    bb.sel = (int*)(wb + L.sel);
+    bb.mean = (double*)(wb + L.mean);
+    bb.sd = (double*)(wb + L.sd);
+    double* rank_b_batch = rank_b ? rank_b + (size_t)p0 * M : nullptr;
+
+    // ---- distribution sort: sample -> histogram -> offsets -> partition -> on-chip finish ----
+    const dim3 gc(L.nchunks, PB);
+    LAUNCH(K_SAMPLE, st, k_sample<<<PB, 512, 0, st>>>(xb, (uint32_t)M, bb));
+    LAUNCH(K_BHIST, st, k_bhist<<<gc, PART_NT, 0, st>>>(xb, (uint32_t)M, L.nchunks, bb));
+    LAUNCH(K_BSCAN, st, k_bscan<<<PB, NB1_MAX, 0, st>>>((uint32_t)M, L.nchunks, bb));
+    LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
+    LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1, PB), FIN_NT, 0, st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
+
+    // ---- LSD fallback for parameters the bucket function could not balance (flag-gated) ----
     SortBufs sb;
-    sb.key[0] = (uint64_t*)(wb + L.key0);
-    sb.key[1] = (uint64_t*)(wb + L.key1);
-    sb.idx[0] = (uint32_t*)(wb + L.idx0);
-    sb.idx[1] = (uint32_t*)(wb + L.idx1);
+    sb.key[0] = bb.pkey; sb.key[1] = bb.skey;
+    sb.idx[0] = bb.pidx; sb.idx[1] = bb.sidx;
     sb.hist = (uint32_t*)(wb + L.hist);
-    sb.sel = (int*)(wb + L.sel);
+    sb.sel = bb.sel;
     sb.sum = (double*)(wb + L.sum);
     sb.flag = flag;
+    sb.only = bb.fallback;
     LAUNCH(K_HIST0, st, k_hist0<<<PB, 1024, 0, st>>>(xb, (uint32_t)M, sb));
     LAUNCH(K_RADIX, st, k_radix_pass<true><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, 0, sb));
-    for (int pass = 1; pass < 8; ++pass) {
+    for (int pass = 1; pass < 8; ++pass)
       LAUNCH(K_RADIX, st, k_radix_pass<false><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, pass, sb));
-    }
+
     RankBufs rb;
     rb.key[0] = sb.key[0]; rb.key[1] = sb.key[1];
     rb.idx[0] = sb.idx[0]; rb.idx[1] = sb.idx[1];
     rb.sel = sb.sel;
-    rb.sum = sb.sum;
+    rb.kcode = bb.kcode;
+    rb.fallback = bb.fallback;
     rb.med = (double*)(wb + L.med);
     rb.m0 = (uint32_t*)(wb + L.m0);
     rb.apos = (uint32_t*)(wb + L.apos);
-    rb.sqpart = (double*)(wb + L.sqpart);
     rb.ztab = ztab;
+    const dim3 gt(L.ntiles, PB);
+    LAUNCH(K_RANKC, st, k_rank_codes<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, rank_b_batch));
+
     PrepOut po;
     po.quant = (out && out->quantiles) ? out->quantiles + (size_t)p0 * nq : nullptr;
     po.ostats = (out && out->order_stats) ? out->order_stats + (size_t)p0 * nq * 2 : nullptr;
     po.median = (out && out->median) ? out->median + p0 : nullptr;
-    po.mean = (out && out->mean) ? out->mean + p0 : nullptr;
     LAUNCH(K_PREP, st, k_param_prep<<<(PB + 127) / 128, 128, 0, st>>>(rb, (uint32_t)M, PB, qa, po));
 
-    const dim3 gt(L.ntiles, PB);
-    const bool ranks = mode.diag || mode.want_ranks;
-    double* zb = z_b ? z_b + (size_t)p0 * M : (need_z ? (double*)(wb + L.zb) : nullptr);
-    double* zf = z_f ? z_f + (size_t)p0 * M : (need_z ? (double*)(wb + L.zf) : nullptr);
-    if (ranks) {
-      ScatterOut so{zb, rank_b ? rank_b + (size_t)p0 * M : nullptr};
-      LAUNCH(K_RANK, st, k_rank<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, so));
-      if (mode.diag || zf || rank_f) {
-        LAUNCH(K_MPART, st, k_merge_partition<<<dim3((L.ntiles + 1 + 127) / 128, PB), 128, 0, st>>>(rb, (uint32_t)M, L.ntiles, PB));
-        ScatterOut sf{zf, rank_f ? rank_f + (size_t)p0 * M : nullptr};
-        LAUNCH(K_FOLD, st, k_fold<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, sf));
-      }
-    } else {
-      LAUNCH(K_SUMSQ, st, k_sumsq<<<gt, RANK_NT, 0, st>>>(xb, (uint32_t)M, L.ntiles, sb.sum, rb.sqpart));
+    double2* zz = ws_zz ? (double2*)(wb + L.zz) : nullptr;
+    if (want_scores) {
+      LAUNCH(K_MPART, st, k_merge_partition<<<dim3((L.ntiles + 1 + 127) / 128, PB), 128, 0, st>>>(rb, (uint32_t)M, L.ntiles, PB));
+      FoldOut fo;
+      fo.zz = zz;
+      fo.z = z_b ? z_b + (size_t)p0 * M : nullptr;
+      fo.zf = z_f ? z_f + (size_t)p0 * M : nullptr;
+      fo.rankf = rank_f ? rank_f + (size_t)p0 * M : nullptr;
+      LAUNCH(K_FOLD, st, k_fold<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, fo));
     }
     ChainOut co{(double*)(wb + L.crhat), (double*)(wb + L.cess), (int64_t*)(wb + L.clag)};
-    if (mode.diag) {
-      LAUNCH(K_CHAIN, st, k_chain<<<dim3(PB, 2), CH_NT, chain_smem, st>>>(zb, zf, (uint32_t)C, (uint32_t)N, PB, co));
-    }
+    if (mode.diag)
+      LAUNCH(K_CHAIN, st, k_chain<<<2 * PB, CH_NT, chain_smem, st>>>((const double*)zz, (uint32_t)C, (uint32_t)N, PB, co));
     if (out) {
       FinalizeArgs fa;
       memset(&fa, 0, sizeof(fa));
-      fa.sum = sb.sum;
-      fa.sqpart = rb.sqpart;
-      fa.ntiles = L.ntiles;
+      fa.mean = bb.mean;
+      fa.sd = bb.sd;
+      fa.mean_out = out->mean ? out->mean + p0 : nullptr;
       fa.std_out = out->std ? out->std + p0 : nullptr;
       if (mode.diag) {
         fa.crhat = co.rhat;

@@ -67,10 +67,12 @@ __device__ __forceinline__ void lag_block_accumulate(const double* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(CH_NT) k_chain(const double* __restrict__ zb, const double* __restrict__ zf,
-                                                 uint32_t C, uint32_t N, int PB, ChainOut out) {
+// zz: [PB][C][N] pairs {z_bulk, z_folded}; CTA (2p + kind) reads component `kind`
+// (the sibling CTA reads the other half of the same sectors -> L2 hit).
+__global__ void __launch_bounds__(CH_NT) k_chain(const double* __restrict__ zz, uint32_t C, uint32_t N, int PB,
+                                                 ChainOut out) {
   extern __shared__ double smem[];
-  const int p = blockIdx.x, kind = blockIdx.y;
+  const int p = blockIdx.x >> 1, kind = blockIdx.x & 1;
   const int tid = threadIdx.x;
   const uint32_t ny = pad_idx(N + 2 * LAGB + CHUNK) + 2;
   double* y = smem;             // padded chain
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(CH_NT) k_chain(const double* __restrict__ zb, 
   __shared__ int s_done;
   __shared__ long long s_lag;
 
-  const double* z = (kind ? zf : zb) + (size_t)p * C * N;
+  const double* z = zz + 2 * (size_t)p * C * N + kind;
   const uint32_t half = N / 2;
   const double dn = (double)N, dh = (double)half;
 
@@ -93,8 +95,8 @@ __global__ void __launch_bounds__(CH_NT) k_chain(const double* __restrict__ zb, 
   // ---- pass 0 over chains: moments + lag block [1, 16] ----
   for (uint32_t c = 0; c < C; ++c) {
     __syncthreads();
-    const double* zc = z + (size_t)c * N;
-    for (uint32_t i = tid; i < N + 2 * LAGB + CHUNK; i += CH_NT) y[pad_idx(i)] = (i < N) ? zc[i] : 0.0;
+    const double* zc = z + 2 * (size_t)c * N;
+    for (uint32_t i = tid; i < N + 2 * LAGB + CHUNK; i += CH_NT) y[pad_idx(i)] = (i < N) ? zc[2 * i] : 0.0;
     __syncthreads();
     double s1 = 0, s2 = 0, s3 = 0;
     for (uint32_t i = tid; i < N; i += CH_NT) {
@@ -173,9 +175,9 @@ __global__ void __launch_bounds__(CH_NT) k_chain(const double* __restrict__ zb, 
       for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
       for (uint32_t c = 0; c < C; ++c) {
         __syncthreads();
-        const double* zc = z + (size_t)c * N;
+        const double* zc = z + 2 * (size_t)c * N;
         const double mf = cmean[c];
-        for (uint32_t i = tid; i < N + 2 * LAGB + CHUNK; i += CH_NT) y[pad_idx(i)] = (i < N) ? zc[i] - mf : 0.0;
+        for (uint32_t i = tid; i < N + 2 * LAGB + CHUNK; i += CH_NT) y[pad_idx(i)] = (i < N) ? zc[2 * i] - mf : 0.0;
         __syncthreads();
         lag_block_accumulate<CH_NT>(y, N, t0, acc);
       }

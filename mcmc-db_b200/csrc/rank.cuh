@@ -4,13 +4,17 @@
 //   k_param_prep      pooled median (statistics.median, diagnostics.py:97), the split
 //                     point of the folded order, numpy-linear quantiles
 //                     (backends_numpy.py:44) and their order statistics.
-//   k_rank            one tile of the sorted keys: tie runs by equality
-//                     (diagnostics.py:113-122), k = i + j, z = T[k], scatter.
+//   k_rank_codes      (LSD fallback path only) one tile of the sorted keys: tie runs
+//                     by equality (diagnostics.py:113-122) -> k = i + j per sorted element.
+//                     The distribution-sort path gets k from k_finish directly.
 //   k_merge_partition merge-path split points of the folded order.
 //   k_fold            folded values |v - med| (diagnostics.py:98) are monotone on each
 //                     side of the median, so their ascending order is the MERGE of the
 //                     reversed left part and the right part of the already sorted
-//                     sequence -- no second sort.  Same tie/z/scatter step.
+//                     sequence -- no second sort.  Tie runs of the folded order, then ONE
+//                     16-byte scatter per draw of {z_bulk, z_folded} to its original
+//                     position (a scattered store costs a full L1 wavefront whatever its
+//                     width, so both scores travel together).
 #pragma once
 #include "as241.cuh"
 #include "common.cuh"
@@ -25,11 +29,11 @@ struct RankBufs {
   const uint64_t* key[2];  // sorted keys are in key[sel[p]]
   const uint32_t* idx[2];
   const int* sel;
-  const double* sum;   // [PB] sum of draws
+  uint32_t* kcode;     // [PB][M] k = i + j per sorted element
+  const uint8_t* fallback;  // [PB] 1 = parameter went through the LSD path
   double* med;         // [PB]
   uint32_t* m0;        // [PB] number of draws strictly below the median
   uint32_t* apos;      // [PB][ntiles+1] merge-path split (count taken from the left part)
-  double* sqpart;      // [PB][ntiles] partial sums of (v - mean)^2
   const double* ztab;  // [2M]
 };
 
@@ -68,7 +72,6 @@ struct PrepOut {
   double* quant;   // [P][nq] or null
   double* ostats;  // [P][nq][2] or null
   double* median;  // [P] or null
-  double* mean;    // [P] or null
 };
 
 struct QuantArgs {
@@ -86,7 +89,6 @@ __global__ void k_param_prep(RankBufs b, uint32_t M, int PB, QuantArgs qa, PrepO
   b.med[p] = med;
   b.m0[p] = lower_bound_u64(keys, 0, M, dbl2key(med));
   if (o.median) o.median[p] = med;
-  if (o.mean) o.mean[p] = b.sum[p] / (double)M;
   for (int i = 0; i < qa.nq; ++i) {
     double os[2];
     const double v = quantile_lerp(keys, M, qa.q[i], os);
@@ -98,7 +100,12 @@ __global__ void k_param_prep(RankBufs b, uint32_t M, int PB, QuantArgs qa, PrepO
   }
 }
 
-// sv[1 + e] = element e of the tile (ascending), sv[0] / sv[n + 1] = neighbours outside
+// padded index for blocked (thread-major) access to 8-byte shared arrays: without it
+// thread t's 8 consecutive elements start 64 B apart -> 16-way bank conflicts.
+__device__ __forceinline__ uint32_t pidx8(uint32_t e) { return e + (e >> 3); }
+constexpr int RANK_SV = RANK_TILE + 2 + (RANK_TILE + 2) / 8 + 2;
+
+// sv[pidx8(1 + e)] = element e of the tile (ascending), sv[0] / sv[pidx8(n + 1)] = neighbours outside
 // the tile (valid iff has_prev / has_next).  Returns k = i + j per item, where
 // [i, j) is the element's tie run in the whole sequence.  ext_i / ext_j are the run
 // bounds of runs that cross the tile's first / last element (only read if needed).
@@ -113,9 +120,9 @@ __device__ __forceinline__ void tie_codes(const uint64_t* sv, uint32_t n, uint32
     hi[it] = 0;
     tj[it] = 0xffffffffu;
     if (e < n) {
-      const uint64_t cur = sv[e + 1];
-      const bool head = (e == 0) ? !(has_prev && sv[0] == cur) : (sv[e] != cur);
-      const bool tail = (e == n - 1) ? !(has_next && sv[n + 1] == cur) : (sv[e + 2] != cur);
+      const uint64_t cur = sv[pidx8(e + 1)];
+      const bool head = (e == 0) ? !(has_prev && sv[0] == cur) : (sv[pidx8(e)] != cur);
+      const bool tail = (e == n - 1) ? !(has_next && sv[pidx8(n + 1)] == cur) : (sv[pidx8(e + 2)] != cur);
       if (head) hi[it] = gbase + e + 1;
       if (tail) tj[it] = gbase + e + 1;
     }
@@ -130,17 +137,13 @@ __device__ __forceinline__ void tie_codes(const uint64_t* sv, uint32_t n, uint32
   }
 }
 
-struct ScatterOut {
-  double* z;     // [PB][M] normal scores in original positions (or null)
-  double* rank;  // [PB][M] average ranks in original positions (or null)
-};
-
-__global__ void __launch_bounds__(RANK_NT) k_rank(RankBufs b, uint32_t M, uint32_t ntiles, ScatterOut o) {
-  __shared__ uint64_t sv[RANK_TILE + 2];
+// LSD fallback path: k = i + j for every sorted element of the flagged parameters.
+__global__ void __launch_bounds__(RANK_NT) k_rank_codes(RankBufs b, uint32_t M, double* rank_out) {
+  __shared__ uint64_t sv[RANK_SV];
   __shared__ uint32_t ext[2];
   __shared__ uint32_t scan_sm[RANK_NT / 32];
-  __shared__ double red[33];
   const int p = blockIdx.y;
+  if (!b.fallback[p]) return;
   const uint32_t tile = blockIdx.x;
   const uint32_t gbase = tile * RANK_TILE;
   const uint32_t n = min((uint32_t)RANK_TILE, M - gbase);
@@ -149,34 +152,27 @@ __global__ void __launch_bounds__(RANK_NT) k_rank(RankBufs b, uint32_t M, uint32
   const uint32_t* idx = b.idx[s] + (size_t)p * M;
   const bool has_prev = gbase > 0, has_next = gbase + n < M;
 
-  for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) sv[e + 1] = keys[gbase + e];
+  for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) sv[pidx8(e + 1)] = keys[gbase + e];
   if (threadIdx.x == 0) sv[0] = has_prev ? keys[gbase - 1] : 0;
-  if (threadIdx.x == 32) sv[n + 1] = has_next ? keys[gbase + n] : 0;
+  if (threadIdx.x == 32) sv[pidx8(n + 1)] = has_next ? keys[gbase + n] : 0;
   __syncthreads();
-  if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[1]) ? lower_bound_u64(keys, 0, gbase, sv[1]) : 0;
+  if (threadIdx.x == 0)
+    ext[0] = (has_prev && sv[0] == sv[pidx8(1)]) ? lower_bound_u64(keys, 0, gbase, sv[pidx8(1)]) : 0;
   if (threadIdx.x == 32)
-    ext[1] = (has_next && sv[n + 1] == sv[n]) ? upper_bound_u64(keys, gbase + n, M, sv[n]) : 0;
+    ext[1] = (has_next && sv[pidx8(n + 1)] == sv[pidx8(n)]) ? upper_bound_u64(keys, gbase + n, M, sv[pidx8(n)]) : 0;
   __syncthreads();
 
   uint32_t k[RANK_IPT];
   tie_codes<RANK_NT, RANK_IPT>(sv, n, gbase, has_prev, has_next, ext, scan_sm, k);
-
-  const double mean = b.sum[p] / (double)M;
-  double sq = 0.0;
-  const size_t pbase = (size_t)p * M;
+  uint32_t* kc = b.kcode + (size_t)p * M;
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
     const uint32_t e = threadIdx.x * RANK_IPT + it;
     if (e < n) {
-      const double d = key2dbl(sv[e + 1]) - mean;
-      sq += d * d;
-      const uint32_t pos = idx[gbase + e];
-      if (o.z) o.z[pbase + pos] = b.ztab[k[it]];
-      if (o.rank) o.rank[pbase + pos] = (double)(k[it] + 1u) * 0.5;
+      kc[gbase + e] = k[it];
+      if (rank_out) rank_out[(size_t)p * M + idx[gbase + e]] = (double)(k[it] + 1u) * 0.5;
     }
   }
-  sq = block_sum<RANK_NT>(sq, red);
-  if (threadIdx.x == 0) b.sqpart[(size_t)p * ntiles + tile] = sq;
 }
 
 // Folded views of the sorted sequence s[0..M): left part reversed and right part,
@@ -228,16 +224,24 @@ __global__ void k_merge_partition(RankBufs b, uint32_t M, uint32_t ntiles, int P
   b.apos[(size_t)p * (ntiles + 1) + q] = f.split(o);
 }
 
-__global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, ScatterOut o) {
+struct FoldOut {
+  double2* zz;         // [PB][M] {z_bulk, z_folded} in original positions (diagnostics path) or null
+  double* z;           // separate outputs (ranks API), any may be null
+  double* zf;
+  double* rankf;
+};
+
+__global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
   __shared__ uint64_t sd[RANK_TILE];      // left window then right window (folded bits)
-  __shared__ uint32_t si[RANK_TILE];      // their original positions
-  __shared__ uint64_t sv[RANK_TILE + 2];  // merged
+  __shared__ uint32_t st[RANK_TILE];      // their positions in the sorted sequence
+  __shared__ uint64_t sv[RANK_SV];        // merged (padded index)
   __shared__ uint32_t ext[2];
   __shared__ uint32_t scan_sm[RANK_NT / 32];
   const int p = blockIdx.y;
   const uint32_t tile = blockIdx.x;
   const int s = b.sel[p];
   const uint32_t* idx = b.idx[s] + (size_t)p * M;
+  const uint32_t* kc = b.kcode + (size_t)p * M;
   FoldView f{b.key[s] + (size_t)p * M, b.m0[p], M, b.med[p]};
   const uint32_t gbase = tile * RANK_TILE;
   const uint32_t n = min((uint32_t)RANK_TILE, M - gbase);
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
   for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) {
     const uint32_t t = (e < nl) ? (f.m0 - 1 - (a0 + e)) : (f.m0 + c0 + (e - nl));
     sd[e] = f.fbits(t);
-    si[e] = idx[t];
+    st[e] = t;
   }
   if (threadIdx.x == 0) {
     // merged element just before the tile: the larger of the two preceding heads
@@ -263,12 +267,12 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
     uint64_t nv = ~0ull;
     if (a1 < f.nL()) nv = f.L(a1);
     if (c1 < f.nR()) nv = min(nv, f.R(c1));
-    sv[n + 1] = nv;
+    sv[pidx8(n + 1)] = nv;
   }
   __syncthreads();
 
   // per-thread merge path inside the tile
-  uint32_t midx[RANK_IPT];
+  uint32_t mt[RANK_IPT];
   {
     const uint32_t od = min((uint32_t)threadIdx.x * RANK_IPT, n);
     uint32_t lo = (od > nr) ? od - nr : 0, hi = min(od, nl);
@@ -280,20 +284,21 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
 #pragma unroll
     for (int it = 0; it < RANK_IPT; ++it) {
       const uint32_t e = od + it;
-      midx[it] = 0;
+      mt[it] = 0;
       if (e < n) {
         const bool takeL = (la < nl) && (lc >= nr || sd[la] <= sd[nl + lc]);
         const uint32_t src = takeL ? la : nl + lc;
-        sv[e + 1] = sd[src];
-        midx[it] = si[src];
+        sv[pidx8(e + 1)] = sd[src];
+        mt[it] = st[src];
         la += takeL ? 1u : 0u;
         lc += takeL ? 0u : 1u;
       }
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[1]) ? f.count_less(sv[1]) : 0;
-  if (threadIdx.x == 32) ext[1] = (has_next && sv[n + 1] == sv[n]) ? f.count_leq(sv[n]) : 0;
+  if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[pidx8(1)]) ? f.count_less(sv[pidx8(1)]) : 0;
+  if (threadIdx.x == 32)
+    ext[1] = (has_next && sv[pidx8(n + 1)] == sv[pidx8(n)]) ? f.count_leq(sv[pidx8(n)]) : 0;
   __syncthreads();
 
   uint32_t k[RANK_IPT];
@@ -303,8 +308,16 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
   for (int it = 0; it < RANK_IPT; ++it) {
     const uint32_t e = threadIdx.x * RANK_IPT + it;
     if (e < n) {
-      if (o.z) o.z[pbase + midx[it]] = b.ztab[k[it]];
-      if (o.rank) o.rank[pbase + midx[it]] = (double)(k[it] + 1u) * 0.5;
+      const uint32_t t = mt[it];
+      const uint32_t pos = idx[t];
+      const double zfv = b.ztab[k[it]];
+      if (o.zz) {
+        o.zz[pbase + pos] = make_double2(b.ztab[kc[t]], zfv);
+      } else {
+        if (o.z) o.z[pbase + pos] = b.ztab[kc[t]];
+        if (o.zf) o.zf[pbase + pos] = zfv;
+        if (o.rankf) o.rankf[pbase + pos] = (double)(k[it] + 1u) * 0.5;
+      }
     }
   }
 }

@@ -27,6 +27,7 @@ struct SortBufs {
   int* sel;           // [PB] which of key[]/idx[] holds the current sequence
   double* sum;        // [PB] sum of the draws (for the mean)
   int* flag;          // bit0: non-finite input seen
+  const uint8_t* only;  // if non-null: process parameter p only when only[p] != 0 (fallback list)
 };
 
 __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid) {
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(1024) k_hist0(const double* __restrict__ x, ui
   __shared__ uint32_t h[4][256];
   __shared__ double red[33];
   const int p = blockIdx.x;
+  if (b.only && !b.only[p]) return;
   const double* xp = x + (size_t)p * M;
   for (int i = threadIdx.x; i < 4 * 256; i += 1024) (&h[0][0])[i] = 0;
   __syncthreads();
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(SORT_NT) k_radix_pass(const double* __restrict
   __shared__ uint32_t hnext[256];
   __shared__ int skip;
   const int p = blockIdx.x;
+  if (b.only && !b.only[p]) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t* hp = b.hist + ((size_t)p * 8 + pass) * 256;
   const int shift = pass * 8;

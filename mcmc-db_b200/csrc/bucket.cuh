@@ -83,6 +83,8 @@ struct BucketBufs {
   uint32_t* boff;      // [PB][NB1_MAX + 1]       bucket start offsets in the sorted order
   double* spart;       // [PB][nchunks][2]        shifted power sums per chunk
   uint8_t* fallback;   // [PB] 1 = sort this parameter with the LSD path
+  int* nfb;            // number of fallback parameters in this batch
+  int* plist;          // [PB] their indices (compact, arbitrary order)
   int* flag;           // bit0 non-finite input
   uint64_t* pkey;      // [PB][M] partitioned keys
   uint32_t* pidx;      // [PB][M] partitioned positions
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     fn->nb1 = nb1;
     b.fallback[p] = 0;
     b.sel[p] = 1;
+    if (p == 0) *b.nfb = 0;
   }
   const double csf = isfinite(cs) ? cs : 0.0;
   for (int j = threadIdx.x; j < NB1_MAX; j += 512) {
@@ -248,7 +251,10 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
     b.sd[p] = sqrt(var > 0.0 ? var : 0.0);
   }
   __syncthreads();
-  if (t == 0 && over) b.fallback[p] = 1;
+  if (t == 0 && over) {
+    b.fallback[p] = 1;
+    b.plist[atomicAdd(b.nfb, 1)] = p;
+  }
 }
 
 // ---------------------------------------------------------------- k_partition

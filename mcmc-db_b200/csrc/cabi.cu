@@ -46,10 +46,10 @@ int fail(int code, const char* fmt, ...) {
 // ---- optional per-kernel timing (bench.py's roofline block): CUDA events recorded on the
 // launching stream around every kernel while enabled.
 enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_HIST0, K_RADIX, K_RANKC, K_PREP,
-                K_MPART, K_FOLD, K_CHAIN, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_COUNT };
+                K_MPART, K_FOLD, K_CHAIN, K_DECIDE, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_sample", "k_bhist", "k_bscan", "k_partition", "k_finish",
                                            "k_hist0", "k_radix_pass", "k_rank_codes", "k_param_prep",
-                                           "k_merge_partition", "k_fold", "k_chain", "k_finalize",
+                                           "k_merge_partition", "k_fold", "k_moments", "k_decide", "k_finalize",
                                            "k_summary", "k_compare", "k_checks", "k_synth"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 bool g_prof = false;
@@ -88,10 +88,10 @@ inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 // Workspace carve-up for one batch of PB parameters with M pooled draws each.
 struct Layout {
   size_t ztab, flag, header;  // shared part
-  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, spart, fallback, hist, sel, sum, mean, sd, med, m0, apos,
-      crhat, cess, clag, per_batch;
+  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, spart, fallback, nfb, plist, hist, sel, sum, mean, sd, med, m0, apos,
+      crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cwl0, cwl1, cnwl, per_batch;
   uint32_t ntiles, nchunks;
-  void compute(int64_t PB, int64_t M, bool diag) {
+  void compute(int64_t PB, int64_t M, bool diag, int64_t C = 1, int64_t N = 1) {
     ntiles = (uint32_t)((M + RANK_TILE - 1) / RANK_TILE);
     nchunks = (uint32_t)((M + CHUNK_P - 1) / CHUNK_P);
     size_t o = 0;
@@ -111,6 +111,8 @@ struct Layout {
     boff = b; b += up((size_t)PB * (NB1_MAX + 1) * 4);
     spart = b; b += up((size_t)PB * nchunks * 2 * 8);
     fallback = b; b += up((size_t)PB);
+    nfb = b; b += up(sizeof(int));
+    plist = b; b += up((size_t)PB * 4);
     hist = b; b += up((size_t)PB * 8 * 256 * 4);
     sel = b; b += up((size_t)PB * 4);
     sum = b; b += up((size_t)PB * 8);
@@ -122,23 +124,39 @@ struct Layout {
     crhat = b; b += up((size_t)PB * 2 * 8);
     cess = b; b += up((size_t)PB * 2 * 8);
     clag = b; b += up((size_t)PB * 2 * 8);
+    if (diag) {
+      const ChainGeom g = chain_geom(C, N);
+      const size_t units = (size_t)C * g.nunits;
+      cpart = b; b += up((size_t)PB * units * 2 * MO_VALS * 8);
+      cpartr = b; b += up((size_t)2 * PB * units * LAGB * 8);
+      cmean = b; b += up((size_t)2 * PB * C * 8);
+      csum = b; b += up((size_t)2 * PB * C * 8);
+      chead = b; b += up((size_t)2 * PB * C * 8);
+      ctail = b; b += up((size_t)2 * PB * C * 8);
+      cvarhat = b; b += up((size_t)2 * PB * 8);
+      crhosum = b; b += up((size_t)2 * PB * 8);
+      cwl0 = b; b += up((size_t)2 * PB * 4);
+      cwl1 = b; b += up((size_t)2 * PB * 4);
+      cnwl = b; b += up(2 * sizeof(int));
+    }
     per_batch = b;
   }
 };
 
 // Largest batch (<= P) whose layout fits in ws_bytes; 0 if not even one parameter fits.
-int64_t fit_batch(int64_t P, int64_t M, bool diag, size_t ws_bytes, int64_t cap) {
+int64_t fit_batch(int64_t P, int64_t M, bool diag, size_t ws_bytes, int64_t cap, int64_t C, int64_t N) {
   int64_t hi = std::min<int64_t>(P, cap), lo = 0;
   Layout l;
   while (lo < hi) {
     const int64_t mid = lo + (hi - lo + 1) / 2;
-    l.compute(mid, M, diag);
+    l.compute(mid, M, diag, C, N);
     if (l.header + l.per_batch <= ws_bytes) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
 
 constexpr int64_t BATCH_CAP = 4096;
+constexpr int FALLBACK_GRID = 296;  // CTAs striding over the fallback list (2 per SM)
 
 // ---- small kernels used only by the orchestration ----
 
@@ -254,19 +272,13 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   if (nq < 0 || nq > B200REF_MAX_QUANTILES) return fail(B200REF_ERR_ARG, "nq=%d out of range", nq);
   if (P == 0) return B200REF_OK;
   if (!ws) return fail(B200REF_ERR_WORKSPACE, "null workspace");
-  size_t chain_smem = 0;
-  if (mode.diag) {
-    chain_smem = chain_smem_bytes(C, N);
-    if (chain_smem > 227 * 1024)
-      return fail(B200REF_ERR_ARG, "N=%lld draws per chain does not fit the on-chip chain buffer", (long long)N);
-    CUDA_TRY(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));
-  }
+  if (mode.diag && C > 4096) return fail(B200REF_ERR_ARG, "more than 4096 chains are not supported (C=%lld)", (long long)C);
   const bool need_z = mode.diag;
   const bool ws_zz = mode.diag;  // interleaved {z_bulk, z_folded} scratch for k_chain
-  const int64_t PBmax = fit_batch(P, M, ws_zz, ws_bytes, BATCH_CAP);
+  const int64_t PBmax = fit_batch(P, M, ws_zz, ws_bytes, BATCH_CAP, C, N);
   if (PBmax < 1) return fail(B200REF_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one parameter", ws_bytes);
   Layout L;
-  L.compute(PBmax, M, ws_zz);
+  L.compute(PBmax, M, ws_zz, C, N);
   char* w = (char*)ws;
   double* ztab = (double*)(w + L.ztab);
   int* flag = (int*)(w + L.flag);
@@ -294,6 +306,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     bb.boff = (uint32_t*)(wb + L.boff);
     bb.spart = (double*)(wb + L.spart);
     bb.fallback = (uint8_t*)(wb + L.fallback);
+    bb.nfb = (int*)(wb + L.nfb);
+    bb.plist = (int*)(wb + L.plist);
     bb.flag = flag;
     bb.pkey = (uint64_t*)(wb + L.pkey);
     bb.pidx = (uint32_t*)(wb + L.pidx);
@@ -321,11 +335,13 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     sb.sel = bb.sel;
     sb.sum = (double*)(wb + L.sum);
     sb.flag = flag;
-    sb.only = bb.fallback;
-    LAUNCH(K_HIST0, st, k_hist0<<<PB, 1024, 0, st>>>(xb, (uint32_t)M, sb));
-    LAUNCH(K_RADIX, st, k_radix_pass<true><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, 0, sb));
+    sb.nlist = bb.nfb;
+    sb.plist = bb.plist;
+    const int fbg = std::min(PB, FALLBACK_GRID);
+    LAUNCH(K_HIST0, st, k_hist0<<<fbg, 1024, 0, st>>>(xb, (uint32_t)M, sb));
+    LAUNCH(K_RADIX, st, k_radix_pass<true><<<fbg, SORT_NT, 0, st>>>(xb, (uint32_t)M, 0, sb));
     for (int pass = 1; pass < 8; ++pass)
-      LAUNCH(K_RADIX, st, k_radix_pass<false><<<PB, SORT_NT, 0, st>>>(xb, (uint32_t)M, pass, sb));
+      LAUNCH(K_RADIX, st, k_radix_pass<false><<<fbg, SORT_NT, 0, st>>>(xb, (uint32_t)M, pass, sb));
 
     RankBufs rb;
     rb.key[0] = sb.key[0]; rb.key[1] = sb.key[1];
@@ -333,12 +349,14 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     rb.sel = sb.sel;
     rb.kcode = bb.kcode;
     rb.fallback = bb.fallback;
+    rb.nfb = bb.nfb;
+    rb.plist = bb.plist;
     rb.med = (double*)(wb + L.med);
     rb.m0 = (uint32_t*)(wb + L.m0);
     rb.apos = (uint32_t*)(wb + L.apos);
     rb.ztab = ztab;
     const dim3 gt(L.ntiles, PB);
-    LAUNCH(K_RANKC, st, k_rank_codes<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, rank_b_batch));
+    LAUNCH(K_RANKC, st, k_rank_codes<<<dim3(L.ntiles, std::min(PB, 8)), RANK_NT, 0, st>>>(rb, (uint32_t)M, rank_b_batch));
 
     PrepOut po;
     po.quant = (out && out->quantiles) ? out->quantiles + (size_t)p0 * nq : nullptr;
@@ -356,9 +374,41 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       fo.rankf = rank_f ? rank_f + (size_t)p0 * M : nullptr;
       LAUNCH(K_FOLD, st, k_fold<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, fo));
     }
-    ChainOut co{(double*)(wb + L.crhat), (double*)(wb + L.cess), (int64_t*)(wb + L.clag)};
-    if (mode.diag)
-      LAUNCH(K_CHAIN, st, k_chain<<<2 * PB, CH_NT, chain_smem, st>>>((const double*)zz, (uint32_t)C, (uint32_t)N, PB, co));
+    ChainState cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.rhat = (double*)(wb + L.crhat);
+    cs.ess = (double*)(wb + L.cess);
+    cs.lag = (int64_t*)(wb + L.clag);
+    if (mode.diag) {
+      // ---- streaming chain statistics: round 0 for everybody, further rounds for sticky chains ----
+      const ChainGeom g = chain_geom(C, N);
+      cs.part = (double*)(wb + L.cpart);
+      cs.partr = (double*)(wb + L.cpartr);
+      cs.cmean = (double*)(wb + L.cmean);
+      cs.csum = (double*)(wb + L.csum);
+      cs.head = (double*)(wb + L.chead);
+      cs.tail = (double*)(wb + L.ctail);
+      cs.varhat = (double*)(wb + L.cvarhat);
+      cs.rhosum = (double*)(wb + L.crhosum);
+      cs.wl[0] = (int*)(wb + L.cwl0);
+      cs.wl[1] = (int*)(wb + L.cwl1);
+      cs.nwl = (int*)(wb + L.cnwl);
+      CUDA_TRY(cudaMemsetAsync(cs.nwl, 0, 2 * sizeof(int), st));
+      if (g.nunits)
+        LAUNCH(K_CHAIN, st, k_moments0<<<dim3((unsigned)(C * g.nunits), PB, 2), MO_NT, 0, st>>>(zz, g, cs.part));
+      LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
+      int cur = 0;
+      for (uint32_t t0 = 1 + LAGB; t0 < (uint32_t)N; t0 += LAGB) {
+        int nwork = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nwork, cs.nwl + cur, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (nwork == 0) break;
+        CUDA_TRY(cudaMemsetAsync(cs.nwl + (cur ^ 1), 0, sizeof(int), st));
+        LAUNCH(K_CHAIN, st, k_moments_r<<<dim3((unsigned)(C * g.nunits), nwork), MO_NT, 0, st>>>(zz, g, t0, cs.wl[cur], cs.partr));
+        LAUNCH(K_DECIDE, st, k_decide_r<<<nwork, DEC_NT, 0, st>>>(zz, g, PB, t0, cur, cs));
+        cur ^= 1;
+      }
+    }
     if (out) {
       FinalizeArgs fa;
       memset(&fa, 0, sizeof(fa));
@@ -367,9 +417,9 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       fa.mean_out = out->mean ? out->mean + p0 : nullptr;
       fa.std_out = out->std ? out->std + p0 : nullptr;
       if (mode.diag) {
-        fa.crhat = co.rhat;
-        fa.cess = co.ess;
-        fa.clag = (const long long*)co.lag;
+        fa.crhat = cs.rhat;
+        fa.cess = cs.ess;
+        fa.clag = (const long long*)cs.lag;
         fa.rhat = out->rhat ? out->rhat + p0 : nullptr;
         fa.rhat_bulk = out->rhat_bulk ? out->rhat_bulk + p0 : nullptr;
         fa.rhat_tail = out->rhat_tail ? out->rhat_tail + p0 : nullptr;
@@ -400,12 +450,12 @@ uint64_t b200ref_kernel_launches(void) { return g_launches.load(); }
 size_t b200ref_workspace_bytes(int64_t P, int64_t C, int64_t N) {
   if (P < 1) P = 1;
   Layout l;
-  l.compute(std::min<int64_t>(P, BATCH_CAP), C * N, true);
+  l.compute(std::min<int64_t>(P, BATCH_CAP), C * N, true, C, N);
   return l.header + l.per_batch;
 }
 size_t b200ref_workspace_min_bytes(int64_t C, int64_t N) {
   Layout l;
-  l.compute(1, C * N, true);
+  l.compute(1, C * N, true, C, N);
   return l.header + l.per_batch;
 }
 

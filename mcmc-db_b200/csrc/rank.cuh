@@ -31,6 +31,8 @@ struct RankBufs {
   const int* sel;
   uint32_t* kcode;     // [PB][M] k = i + j per sorted element
   const uint8_t* fallback;  // [PB] 1 = parameter went through the LSD path
+  const int* nfb;           // number of such parameters
+  const int* plist;         // [*nfb] their indices
   double* med;         // [PB]
   uint32_t* m0;        // [PB] number of draws strictly below the median
   uint32_t* apos;      // [PB][ntiles+1] merge-path split (count taken from the left part)
@@ -142,16 +144,17 @@ __global__ void __launch_bounds__(RANK_NT) k_rank_codes(RankBufs b, uint32_t M, 
   __shared__ uint64_t sv[RANK_SV];
   __shared__ uint32_t ext[2];
   __shared__ uint32_t scan_sm[RANK_NT / 32];
-  const int p = blockIdx.y;
-  if (!b.fallback[p]) return;
+  const int nlist = *b.nfb;
   const uint32_t tile = blockIdx.x;
   const uint32_t gbase = tile * RANK_TILE;
   const uint32_t n = min((uint32_t)RANK_TILE, M - gbase);
+  const bool has_prev = gbase > 0, has_next = gbase + n < M;
+  for (int q = blockIdx.y; q < nlist; q += gridDim.y) {
+  const int p = b.plist[q];
   const int s = b.sel[p];
   const uint64_t* keys = b.key[s] + (size_t)p * M;
   const uint32_t* idx = b.idx[s] + (size_t)p * M;
-  const bool has_prev = gbase > 0, has_next = gbase + n < M;
-
+  __syncthreads();
   for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) sv[pidx8(e + 1)] = keys[gbase + e];
   if (threadIdx.x == 0) sv[0] = has_prev ? keys[gbase - 1] : 0;
   if (threadIdx.x == 32) sv[pidx8(n + 1)] = has_next ? keys[gbase + n] : 0;
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(RANK_NT) k_rank_codes(RankBufs b, uint32_t M, 
       kc[gbase + e] = k[it];
       if (rank_out) rank_out[(size_t)p * M + idx[gbase + e]] = (double)(k[it] + 1u) * 0.5;
     }
+  }
   }
 }
 
@@ -296,28 +300,51 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[pidx8(1)]) ? f.count_less(sv[pidx8(1)]) : 0;
-  if (threadIdx.x == 32)
-    ext[1] = (has_next && sv[pidx8(n + 1)] == sv[pidx8(n)]) ? f.count_leq(sv[pidx8(n)]) : 0;
-  __syncthreads();
 
-  uint32_t k[RANK_IPT];
-  tie_codes<RANK_NT, RANK_IPT>(sv, n, gbase, has_prev, has_next, ext, scan_sm, k);
-  const size_t pbase = (size_t)p * M;
+  // any tie in this tile (or across its edges)?  Continuous draws: almost never.
+  bool tie = false;
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
     const uint32_t e = threadIdx.x * RANK_IPT + it;
-    if (e < n) {
-      const uint32_t t = mt[it];
-      const uint32_t pos = idx[t];
-      const double zfv = b.ztab[k[it]];
-      if (o.zz) {
-        o.zz[pbase + pos] = make_double2(b.ztab[kc[t]], zfv);
-      } else {
-        if (o.z) o.z[pbase + pos] = b.ztab[kc[t]];
-        if (o.zf) o.zf[pbase + pos] = zfv;
-        if (o.rankf) o.rankf[pbase + pos] = (double)(k[it] + 1u) * 0.5;
-      }
+    if (e + 1 < n) tie |= (sv[pidx8(e + 1)] == sv[pidx8(e + 2)]);
+  }
+  if (threadIdx.x == 0) tie |= (has_prev && sv[0] == sv[pidx8(1)]) || (has_next && sv[pidx8(n + 1)] == sv[pidx8(n)]);
+  const int any_tie = __syncthreads_or(tie);
+  uint32_t* sk = reinterpret_cast<uint32_t*>(sd);  // sd is dead after the merge: reuse for k codes
+  if (any_tie) {
+    if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[pidx8(1)]) ? f.count_less(sv[pidx8(1)]) : 0;
+    if (threadIdx.x == 32)
+      ext[1] = (has_next && sv[pidx8(n + 1)] == sv[pidx8(n)]) ? f.count_leq(sv[pidx8(n)]) : 0;
+    __syncthreads();
+    uint32_t k[RANK_IPT];
+    tie_codes<RANK_NT, RANK_IPT>(sv, n, gbase, has_prev, has_next, ext, scan_sm, k);
+#pragma unroll
+    for (int it = 0; it < RANK_IPT; ++it) {
+      const uint32_t e = threadIdx.x * RANK_IPT + it;
+      if (e < n) sk[e] = k[it];
+    }
+  }
+  // st is dead too: it now holds, per merged position, the source position in the sorted sequence
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    const uint32_t e = threadIdx.x * RANK_IPT + it;
+    if (e < n) st[e] = mt[it];
+  }
+  __syncthreads();
+  // striped output: consecutive lanes -> consecutive merged positions, so the table and
+  // (idx, kcode) reads are near-coalesced; only the final 16-byte scatter is random.
+  const size_t pbase = (size_t)p * M;
+  for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) {
+    const uint32_t t = st[e];
+    const uint32_t k = any_tie ? sk[e] : 2u * (gbase + e) + 1u;
+    const uint32_t pos = idx[t];
+    const double zfv = b.ztab[k];
+    if (o.zz) {
+      o.zz[pbase + pos] = make_double2(b.ztab[kc[t]], zfv);
+    } else {
+      if (o.z) o.z[pbase + pos] = b.ztab[kc[t]];
+      if (o.zf) o.zf[pbase + pos] = zfv;
+      if (o.rankf) o.rankf[pbase + pos] = (double)(k + 1u) * 0.5;
     }
   }
 }

@@ -1,7 +1,9 @@
 // Segmented (one segment = one parameter's pooled M = C*N draws) LSD radix sort of
 // (key64, position32) pairs.  One CTA owns one parameter for the whole sort, so
 // digit offsets are carried in shared memory from tile to tile and no cross-CTA
-// look-back is needed; the grid is the parameter batch.
+// look-back is needed.  Since the distribution sort (bucket.cuh) became the main path this
+// is the FALLBACK: a fixed small grid strides over the compact list of parameters whose
+// data defeated the bucket function (empty list -> the launches return at once).
 //
 // This is the ordering step of _rank_normalize (diagnostics.py:110) and of
 // np.quantile / statistics.median (backends_numpy.py:44, diagnostics.py:97).
@@ -27,7 +29,8 @@ struct SortBufs {
   int* sel;           // [PB] which of key[]/idx[] holds the current sequence
   double* sum;        // [PB] sum of the draws (for the mean)
   int* flag;          // bit0: non-finite input seen
-  const uint8_t* only;  // if non-null: process parameter p only when only[p] != 0 (fallback list)
+  const int* nlist;   // number of parameters to sort (device counter)
+  const int* plist;   // [*nlist] their indices; CTAs stride over this list
 };
 
 __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid) {
@@ -42,11 +45,9 @@ __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t d, bool valid) {
 }
 
 // Reads x[p][0..M) once: histograms of digits 0,5,6,7, sum, finiteness.
-__global__ void __launch_bounds__(1024) k_hist0(const double* __restrict__ x, uint32_t M, SortBufs b) {
+__device__ __forceinline__ void hist0_body(const double* __restrict__ x, uint32_t M, const SortBufs& b, int p) {
   __shared__ uint32_t h[4][256];
   __shared__ double red[33];
-  const int p = blockIdx.x;
-  if (b.only && !b.only[p]) return;
   const double* xp = x + (size_t)p * M;
   for (int i = threadIdx.x; i < 4 * 256; i += 1024) (&h[0][0])[i] = 0;
   __syncthreads();
@@ -79,17 +80,23 @@ __global__ void __launch_bounds__(1024) k_hist0(const double* __restrict__ x, ui
   }
 }
 
+__global__ void __launch_bounds__(1024) k_hist0(const double* __restrict__ x, uint32_t M, SortBufs b) {
+  const int n = *b.nlist;
+  for (int q = blockIdx.x; q < n; q += gridDim.x) {
+    hist0_body(x, M, b, b.plist[q]);
+    __syncthreads();
+  }
+}
+
 // One LSD pass for digit `pass` (stable).  FIRST: source is the raw draws
 // (key transform on the fly, position = index); otherwise the current buffer.
 template <bool FIRST>
-__global__ void __launch_bounds__(SORT_NT) k_radix_pass(const double* __restrict__ x, uint32_t M, int pass,
-                                                        SortBufs b) {
+__device__ __forceinline__ void radix_pass_body(const double* __restrict__ x, uint32_t M, int pass,
+                                                const SortBufs& b, int p) {
   __shared__ uint32_t wcnt[SORT_NW][256];
   __shared__ uint32_t base[256];
   __shared__ uint32_t hnext[256];
   __shared__ int skip;
-  const int p = blockIdx.x;
-  if (b.only && !b.only[p]) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t* hp = b.hist + ((size_t)p * 8 + pass) * 256;
   const int shift = pass * 8;
@@ -196,6 +203,16 @@ __global__ void __launch_bounds__(SORT_NT) k_radix_pass(const double* __restrict
   }
   if (want_next && tid < 256) b.hist[((size_t)p * 8 + pass + 1) * 256 + tid] = hnext[tid];
   if (tid == 0) b.sel[p] = dst;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(SORT_NT) k_radix_pass(const double* __restrict__ x, uint32_t M, int pass,
+                                                        SortBufs b) {
+  const int n = *b.nlist;
+  for (int q = blockIdx.x; q < n; q += gridDim.x) {
+    radix_pass_body<FIRST>(x, M, pass, b, b.plist[q]);
+    __syncthreads();
+  }
 }
 
 }  // namespace b200ref

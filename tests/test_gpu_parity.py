@@ -247,6 +247,20 @@ def test_seeded_against_oracle(B, shape):
     print(f"shape {shape}: mean fraction of tail z bit-equal to the stdlib = {np.mean(fr):.4f}")
 
 
+def test_long_sticky_chains_many_rounds(B):
+    """Chains far longer than any on-chip buffer, and autocorrelation that needs hundreds of lags."""
+    rng = np.random.default_rng(99)
+    c, n = 4, 50001
+    x = np.stack([_ar1(rng, c, n, 0.99), 5.0 + 0.1 * _ar1(rng, c, n, 0.9), _ar1(rng, c, n, 0.0)])
+    d = B.diagnostics_batch(x)
+    for i in range(3):
+        want = O.diagnostics_param(x[i])
+        for k in ("rhat", "ess_bulk", "ess_tail"):
+            assert close(float(d[k][i].item()), want[k], TOL), (i, k, float(d[k][i].item()), want[k])
+        assert int(d["lag_bulk"][i].item()) == want["lag_bulk"] and int(d["lag_tail"][i].item()) == want["lag_tail"]
+    assert int(d["lag_bulk"][0].item()) > 100  # really went through many 16-lag rounds
+
+
 def test_edge_cases(B):
     rng = np.random.default_rng(5)
     cases = {

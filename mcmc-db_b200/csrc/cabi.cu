@@ -82,6 +82,21 @@ inline void prof_end(cudaStream_t st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);     \
   } while (0)
 
+// Side stream for the (rare) LSD fallback, one per host thread.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream& side_stream() {
+  thread_local SideStream ss;
+  if (!ss.s) {
+    cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming);
+  }
+  return ss;
+}
+
 constexpr size_t ALIGN = 256;
 inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 
@@ -324,10 +339,11 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     LAUNCH(K_SAMPLE, st, k_sample<<<PB, 512, 0, st>>>(xb, (uint32_t)M, bb));
     LAUNCH(K_BHIST, st, k_bhist<<<gc, PART_NT, 0, st>>>(xb, (uint32_t)M, L.nchunks, bb));
     LAUNCH(K_BSCAN, st, k_bscan<<<PB, NB1_MAX, 0, st>>>((uint32_t)M, L.nchunks, bb));
-    LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
-    LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1, PB), FIN_NT, 0, st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
 
-    // ---- LSD fallback for parameters the bucket function could not balance (flag-gated) ----
+    // ---- distribution sort, second half (main stream) ----
+    // ---- LSD fallback for parameters the bucket function could not balance: a fixed small grid
+    //      strides over the (usually empty) list, on a side stream, overlapped with k_partition /
+    //      k_finish which skip those parameters. ----
     SortBufs sb;
     sb.key[0] = bb.pkey; sb.key[1] = bb.skey;
     sb.idx[0] = bb.pidx; sb.idx[1] = bb.sidx;
@@ -337,12 +353,6 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     sb.flag = flag;
     sb.nlist = bb.nfb;
     sb.plist = bb.plist;
-    const int fbg = std::min(PB, FALLBACK_GRID);
-    LAUNCH(K_HIST0, st, k_hist0<<<fbg, 1024, 0, st>>>(xb, (uint32_t)M, sb));
-    LAUNCH(K_RADIX, st, k_radix_pass<true><<<fbg, SORT_NT, 0, st>>>(xb, (uint32_t)M, 0, sb));
-    for (int pass = 1; pass < 8; ++pass)
-      LAUNCH(K_RADIX, st, k_radix_pass<false><<<fbg, SORT_NT, 0, st>>>(xb, (uint32_t)M, pass, sb));
-
     RankBufs rb;
     rb.key[0] = sb.key[0]; rb.key[1] = sb.key[1];
     rb.idx[0] = sb.idx[0]; rb.idx[1] = sb.idx[1];
@@ -356,7 +366,21 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     rb.apos = (uint32_t*)(wb + L.apos);
     rb.ztab = ztab;
     const dim3 gt(L.ntiles, PB);
-    LAUNCH(K_RANKC, st, k_rank_codes<<<dim3(L.ntiles, std::min(PB, 8)), RANK_NT, 0, st>>>(rb, (uint32_t)M, rank_b_batch));
+    {
+      SideStream& ss = side_stream();
+      CUDA_TRY(cudaEventRecord(ss.fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(ss.s, ss.fork, 0));
+      const int fbg = std::min(PB, FALLBACK_GRID);
+      LAUNCH(K_HIST0, ss.s, k_hist0<<<fbg, 1024, 0, ss.s>>>(xb, (uint32_t)M, sb));
+      LAUNCH(K_RADIX, ss.s, k_radix_pass<true><<<fbg, SORT_NT, 0, ss.s>>>(xb, (uint32_t)M, 0, sb));
+      for (int pass = 1; pass < 8; ++pass)
+        LAUNCH(K_RADIX, ss.s, k_radix_pass<false><<<fbg, SORT_NT, 0, ss.s>>>(xb, (uint32_t)M, pass, sb));
+      LAUNCH(K_RANKC, ss.s, k_rank_codes<<<dim3(L.ntiles, std::min(PB, 8)), RANK_NT, 0, ss.s>>>(rb, (uint32_t)M, rank_b_batch));
+      CUDA_TRY(cudaEventRecord(ss.join, ss.s));
+    }
+    LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
+    LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1, PB), FIN_NT, 0, st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
+    CUDA_TRY(cudaStreamWaitEvent(st, side_stream().join, 0));
 
     PrepOut po;
     po.quant = (out && out->quantiles) ? out->quantiles + (size_t)p0 * nq : nullptr;

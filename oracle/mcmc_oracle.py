@@ -204,7 +204,12 @@ def _variance_rows(a: np.ndarray) -> np.ndarray:
     if n < 2:
         return np.zeros(a.shape[0])
     mean = a.sum(axis=1) / n
-    return ((a - mean[:, None]) ** 2).sum(axis=1) / (n - 1)
+    var = ((a - mean[:, None]) ** 2).sum(axis=1) / (n - 1)
+    # A constant row has variance exactly 0 in the reference (Python's compensated sum()
+    # returns n*c exactly, so mean == c); numpy's pairwise mean can be 1 ulp off and would
+    # leave ~1e-33 here, turning the reference's R-hat = inf into ~1e16.
+    var[a.max(axis=1) == a.min(axis=1)] = 0.0
+    return var
 
 
 def rhat(chains: np.ndarray) -> float:

@@ -135,6 +135,9 @@ def make_ref_cases():
     cases.append(_case("antithetic_4x80", _ar1(rng, 4, 80, -0.6).tolist()))
     cases.append(_case("huge_range", (10.0 ** rng.uniform(-200, 200, (4, 32)) * rng.choice([-1, 1], (4, 32))).tolist()))
     cases.append(_case("exp_skew_10x100", rng.exponential(2.0, (10, 100)).tolist()))
+    cases.append(_case("constant_chains_4x30", [[0.0] * 30, [1.0] * 30, [0.0] * 30, [1.0] * 30]))
+    cases.append(_case("constant_chains_4x1500", [[0.0] * 1500, [0.0] * 1500, [1.0] * 1500, [1.0] * 1500]))
+    cases.append(_case("constant_chains_5x7", [[0.3] * 7, [0.1] * 7, [0.7] * 7, [0.1] * 7, [0.3] * 7]))
     (HERE / "ref_cases.json").write_text(json.dumps(cases))
     return len(cases)
 

@@ -28,7 +28,11 @@ namespace b200ref {
 
 constexpr int NB1_MAX = 256;      // coarse buckets per parameter (power of two, <= 256)
 constexpr int NCELL = 1024;       // linear cells of the splitter lookup table
-constexpr int NFINE = 256;        // fine buckets per coarse bucket
+constexpr int NFINE = 512;        // fine buckets per coarse bucket
+constexpr int CAPBIG = 12288;     // oversize coarse buckets up to this many draws: k_finish_big
+constexpr int NFINE_BIG = 2048;
+constexpr int FINB_NT = 1024;
+constexpr int BIGLIST_PER_PARAM = 64;
 constexpr int CAP1 = 2048;        // draws a coarse bucket may hold (on-chip capacity of k_finish)
 constexpr int OVERSAMPLE = 16;    // samples per coarse bucket
 constexpr int CHUNK_P = 4096;     // draws per partition chunk
@@ -83,6 +87,9 @@ struct BucketBufs {
   uint32_t* boff;      // [PB][NB1_MAX + 1]       bucket start offsets in the sorted order
   double* spart;       // [PB][nchunks][2]        shifted power sums per chunk
   uint8_t* fallback;   // [PB] 1 = sort this parameter with the LSD path
+  int* nbigb;          // number of oversize coarse buckets in this batch
+  int* biglist;        // [PB * BIGLIST_PER_PARAM][2] (parameter, coarse bucket)
+  int biglist_cap;
   int* nfb;            // number of fallback parameters in this batch
   int* plist;          // [PB] their indices (compact, arbitrary order)
   int* flag;           // bit0 non-finite input
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     fn->nb1 = nb1;
     b.fallback[p] = 0;
     b.sel[p] = 1;
-    if (p == 0) *b.nfb = 0;
+    if (p == 0) { *b.nfb = 0; *b.nbigb = 0; }
   }
   const double csf = isfinite(cs) ? cs : 0.0;
   for (int j = threadIdx.x; j < NB1_MAX; j += 512) {
@@ -206,6 +213,8 @@ __global__ void __launch_bounds__(PART_NT) k_bhist(const double* __restrict__ x,
 }
 
 // ---------------------------------------------------------------- k_bscan
+static_assert(NB1_MAX == 256 && PART_NT == NB1_MAX, "thread counts double as bin counts");
+
 __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks, BucketBufs b) {
   __shared__ uint32_t wtot[NB1_MAX / 32];
   __shared__ int over;
@@ -220,7 +229,13 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
     cnt[(size_t)c * NB1_MAX + t] = run;
     run += v;
   }
-  if (run > (uint32_t)CAP1) over = 1;
+  if (run > (uint32_t)CAPBIG) {
+    over = 1;
+  } else if (run > (uint32_t)CAP1) {
+    const int slot = atomicAdd(b.nbigb, 1);
+    if (slot < b.biglist_cap) { b.biglist[2 * slot] = p; b.biglist[2 * slot + 1] = t; }
+    else over = 1;  // list full: sort the whole parameter by the LSD path instead
+  }
   // exclusive scan of the bucket totals over the 256 threads
   const int lane = t & 31, w = t >> 5;
   uint32_t incl = run;
@@ -354,79 +369,112 @@ __global__ void __launch_bounds__(PART_NT) k_partition(const double* __restrict_
   }
 }
 
-// ---------------------------------------------------------------- k_finish
+// ---------------------------------------------------------------- k_finish / k_finish_big
 struct FinishOut {
   double* rank;   // optional [PB][M]: average ranks scattered to original positions (ranks API)
 };
 
-static_assert(FIN_NT == NFINE && NB1_MAX == 256 && PART_NT == NB1_MAX, "thread counts double as bin counts");
+// Shared-memory layout of one finishing CTA (dynamic).
+template <int CAP, int NF>
+struct FinSmem {
+  double kd[CAP];          // canonical values in fine-bucket order
+  uint32_t i2[CAP];        // their original positions
+  uint32_t fh[NF];         // fine histogram, then running cursors (two-pass mode)
+  uint32_t foff[NF + 1];   // exclusive offsets
+  uint32_t wtot[32];
+  uint32_t bigq[NF];       // fine buckets larger than BIG_FINE
+  uint32_t nbig;
+};
 
-__global__ void __launch_bounds__(FIN_NT) k_finish(uint32_t M, BucketBufs b, FinishOut fo) {
-  __shared__ uint64_t k2[CAP1];
-  __shared__ uint32_t i2[CAP1];
-  __shared__ uint32_t fh[NFINE];
-  __shared__ uint32_t foff[NFINE + 1];
-  __shared__ uint32_t wtot[FIN_NT / 32];
-  __shared__ uint32_t bigq[NFINE];
-  __shared__ uint32_t nbig;
-  const int p = blockIdx.y;
-  if (b.fallback[p]) return;
-  const int cb = blockIdx.x;
-  const BucketFn* fn = b.fn + p;
-  if (cb >= fn->nb1) return;
-  const uint32_t B0 = b.boff[(size_t)p * (NB1_MAX + 1) + cb];
-  const uint32_t n = b.boff[(size_t)p * (NB1_MAX + 1) + cb + 1] - B0;
-  if (n == 0) return;
+// Exclusive scan of fh[NF] -> foff[NF + 1] with NT threads (NF / NT consecutive bins each);
+// also queues the fine buckets that need the warp-cooperative path.
+template <int NT, int NF, int CAP>
+__device__ __forceinline__ void fine_scan(FinSmem<CAP, NF>& sm) {
+  constexpr int PER = NF / NT;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  uint32_t c[PER];
+  uint32_t tsum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { c[k] = sm.fh[tid * PER + k]; tsum += c[k]; }
+  uint32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t nn = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += nn;
+  }
+  if (lane == 31) sm.wtot[w] = incl;
+  __syncthreads();
+  uint32_t pre = 0;
+  for (int k = 0; k < w; ++k) pre += sm.wtot[k];
+  uint32_t run = pre + incl - tsum;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    sm.foff[tid * PER + k] = run;
+    if (c[k] > (uint32_t)BIG_FINE) sm.bigq[atomicAdd(&sm.nbig, 1u)] = tid * PER + k;
+    run += c[k];
+  }
+  if (tid == NT - 1) sm.foff[NF] = run;
+}
+
+// Rank every draw of one coarse bucket (n draws, sorted offset B0) exactly.
+// TWO_PASS = false: the bucket is read once into registers (n <= NT * IPT);
+// TWO_PASS = true : any n <= CAP, the bucket is read twice and slots come from cursors.
+template <int NT, int NF, int CAP, int IPT, bool TWO_PASS>
+__device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const BucketFn* fn, int cb, uint32_t B0, uint32_t n,
+                                              uint32_t M, int p, const BucketBufs& b, const FinishOut& fo) {
   const int tid = threadIdx.x;
-  // bounds of this coarse bucket for the fine level
   const double L = (cb == 0) ? fn->lo : fn->sp[cb - 1];
   const double U = (cb == fn->nb1 - 1) ? fn->hi : fn->sp[cb];
-  double fs = (U > L) ? (double)NFINE / (U - L) : 0.0;
+  double fs = (U > L) ? (double)NF / (U - L) : 0.0;
   if (!isfinite(fs)) fs = 0.0;
-  fh[tid] = 0;
-  if (tid == 0) nbig = 0;
+  auto fine = [&](double x) -> int {
+    const double t = (x - L) * fs;
+    return (t >= 0.0) ? ((t < (double)NF) ? (int)t : NF - 1) : 0;
+  };
+  for (int i = tid; i < NF; i += NT) sm.fh[i] = 0;
+  if (tid == 0) sm.nbig = 0;
   __syncthreads();
   const uint64_t* pk = b.pkey + (size_t)p * M + B0;
   const uint32_t* pi = b.pidx + (size_t)p * M + B0;
-  uint64_t key[FIN_IPT];
-  uint32_t idx[FIN_IPT], r[FIN_IPT];
-  uint16_t f[FIN_IPT];
+  if (!TWO_PASS) {
+    double v[IPT];
+    uint32_t idx[IPT], r[IPT];
+    uint16_t f[IPT];
 #pragma unroll
-  for (int it = 0; it < FIN_IPT; ++it) {
-    const uint32_t e = it * FIN_NT + tid;
-    if (e < n) {
-      key[it] = pk[e];
-      idx[it] = pi[e];
-      f[it] = (uint16_t)fine_of(key2dbl(key[it]), L, fs);
-      r[it] = atomicAdd(&fh[f[it]], 1u);
+    for (int it = 0; it < IPT; ++it) {
+      const uint32_t e = it * NT + tid;
+      if (e < n) {
+        v[it] = key2dbl(pk[e]);
+        idx[it] = pi[e];
+        f[it] = (uint16_t)fine(v[it]);
+        r[it] = atomicAdd(&sm.fh[f[it]], 1u);
+      }
     }
-  }
-  __syncthreads();
-  {
-    const int lane = tid & 31, w = tid >> 5;
-    const uint32_t c = fh[tid];
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t nn = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += nn;
-    }
-    if (lane == 31) wtot[w] = incl;
     __syncthreads();
-    uint32_t pre = 0;
-    for (int k = 0; k < w; ++k) pre += wtot[k];
-    foff[tid] = pre + incl - c;
-    if (tid == NFINE - 1) foff[NFINE] = pre + incl;
-    if (c > (uint32_t)BIG_FINE) bigq[atomicAdd(&nbig, 1u)] = tid;
-  }
-  __syncthreads();
+    fine_scan<NT, NF, CAP>(sm);
+    __syncthreads();
 #pragma unroll
-  for (int it = 0; it < FIN_IPT; ++it) {
-    const uint32_t e = it * FIN_NT + tid;
-    if (e < n) {
-      const uint32_t slot = foff[f[it]] + r[it];
-      k2[slot] = key[it];
-      i2[slot] = idx[it];
+    for (int it = 0; it < IPT; ++it) {
+      const uint32_t e = it * NT + tid;
+      if (e < n) {
+        const uint32_t slot = sm.foff[f[it]] + r[it];
+        sm.kd[slot] = v[it];
+        sm.i2[slot] = idx[it];
+      }
+    }
+  } else {
+    for (uint32_t e = tid; e < n; e += NT) atomicAdd(&sm.fh[fine(key2dbl(pk[e]))], 1u);
+    __syncthreads();
+    fine_scan<NT, NF, CAP>(sm);
+    __syncthreads();
+    for (int i = tid; i < NF; i += NT) sm.fh[i] = 0;  // now cursors
+    __syncthreads();
+    for (uint32_t e = tid; e < n; e += NT) {
+      const double v = key2dbl(pk[e]);
+      const int f = fine(v);
+      const uint32_t slot = sm.foff[f] + atomicAdd(&sm.fh[f], 1u);
+      sm.kd[slot] = v;
+      sm.i2[slot] = pi[e];
     }
   }
   __syncthreads();
@@ -434,58 +482,94 @@ __global__ void __launch_bounds__(FIN_NT) k_finish(uint32_t M, BucketBufs b, Fin
   uint32_t* oi = b.sidx + (size_t)p * M;
   uint32_t* oc = b.kcode + (size_t)p * M;
   double* orank = fo.rank ? fo.rank + (size_t)p * M : nullptr;
-  // small fine buckets: one thread per slot scans its fine bucket
-  for (uint32_t s = tid; s < n; s += FIN_NT) {
-    const uint64_t k = k2[s];
-    const int fb = fine_of(key2dbl(k), L, fs);
-    const uint32_t a = foff[fb], e = foff[fb + 1];
+  // small fine buckets: one thread per slot counts the smaller / equal values of its bucket
+  for (uint32_t s = tid; s < n; s += NT) {
+    const double k = sm.kd[s];
+    const int fb = fine(k);
+    const uint32_t a = sm.foff[fb], e = sm.foff[fb + 1];
     if (e - a > (uint32_t)BIG_FINE) continue;
     uint32_t less = 0, eq = 0, eqb = 0;
     for (uint32_t t = a; t < e; ++t) {
-      const uint64_t kt = k2[t];
+      const double kt = sm.kd[t];
       less += (kt < k);
-      eq += (kt == k);
-      eqb += (kt == k && t < s);
+      const bool same = (kt == k);
+      eq += same;
+      eqb += (same && t < s);
     }
     const uint32_t i = B0 + a + less;
     const uint32_t pos = i + eqb;
-    ok[pos] = k;
-    oi[pos] = i2[s];
+    ok[pos] = dbl2key(k);
+    oi[pos] = sm.i2[s];
     oc[pos] = 2 * i + eq;  // i + j with j = i + eq
-    if (orank) orank[i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
+    if (orank) orank[sm.i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
   }
   // big fine buckets (heavy ties or a density spike): one warp per bucket
-  const uint32_t nb = nbig;
+  const uint32_t nb = sm.nbig;
   const int lane = tid & 31, w = tid >> 5;
-  for (uint32_t q = w; q < nb; q += FIN_NT / 32) {
-    const int fb = bigq[q];
-    const uint32_t a = foff[fb], e = foff[fb + 1];
-    uint64_t mn = ~0ull, mx = 0;
-    for (uint32_t t = a + lane; t < e; t += 32) { const uint64_t kt = k2[t]; mn = min(mn, kt); mx = max(mx, kt); }
+  for (uint32_t q = w; q < nb; q += NT / 32) {
+    const int fb = sm.bigq[q];
+    const uint32_t a = sm.foff[fb], e = sm.foff[fb + 1];
+    double mn = sm.kd[a], mx = mn;
+    for (uint32_t t = a + lane; t < e; t += 32) { const double kt = sm.kd[t]; mn = fmin(mn, kt); mx = fmax(mx, kt); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      mn = min(mn, __shfl_xor_sync(FULL, mn, o));
-      mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+      mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
+      mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
     }
     for (uint32_t s = a + lane; s < e; s += 32) {
-      const uint64_t k = k2[s];
+      const double k = sm.kd[s];
       uint32_t less = 0, eq = e - a, eqb = s - a;
       if (mn != mx) {
         less = 0; eq = 0; eqb = 0;
         for (uint32_t t = a; t < e; ++t) {
-          const uint64_t kt = k2[t];
+          const double kt = sm.kd[t];
           less += (kt < k);
-          eq += (kt == k);
-          eqb += (kt == k && t < s);
+          const bool same = (kt == k);
+          eq += same;
+          eqb += (same && t < s);
         }
       }
       const uint32_t i = B0 + a + less;
       const uint32_t pos = i + eqb;
-      ok[pos] = k;
-      oi[pos] = i2[s];
+      ok[pos] = dbl2key(k);
+      oi[pos] = sm.i2[s];
       oc[pos] = 2 * i + eq;
-      if (orank) orank[i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
+      if (orank) orank[sm.i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
     }
+  }
+}
+
+using FinSmemSmall = FinSmem<CAP1, NFINE>;
+using FinSmemBig = FinSmem<CAPBIG, NFINE_BIG>;
+
+// one CTA per coarse bucket of at most CAP1 draws
+__global__ void __launch_bounds__(FIN_NT, 4) k_finish(uint32_t M, BucketBufs b, FinishOut fo) {
+  extern __shared__ __align__(16) unsigned char fin_smem_raw[];
+  FinSmemSmall& sm = *reinterpret_cast<FinSmemSmall*>(fin_smem_raw);
+  const int p = blockIdx.y;
+  if (b.fallback[p]) return;
+  const int cb = blockIdx.x;
+  const BucketFn* fn = b.fn + p;
+  if (cb >= fn->nb1) return;
+  const uint32_t B0 = b.boff[(size_t)p * (NB1_MAX + 1) + cb];
+  const uint32_t n = b.boff[(size_t)p * (NB1_MAX + 1) + cb + 1] - B0;
+  if (n == 0 || n > (uint32_t)CAP1) return;  // oversize buckets: k_finish_big
+  finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, fn, cb, B0, n, M, p, b, fo);
+}
+
+// oversize coarse buckets (CAP1 < n <= CAPBIG: a few heavily repeated values): a small grid
+// strides over the list k_bscan built
+__global__ void __launch_bounds__(FINB_NT) k_finish_big(uint32_t M, BucketBufs b, FinishOut fo) {
+  extern __shared__ __align__(16) unsigned char fin_smem_raw[];
+  FinSmemBig& sm = *reinterpret_cast<FinSmemBig*>(fin_smem_raw);
+  const int nbig = *b.nbigb;
+  for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
+    const int p = b.biglist[2 * q], cb = b.biglist[2 * q + 1];
+    if (b.fallback[p]) continue;
+    const uint32_t B0 = b.boff[(size_t)p * (NB1_MAX + 1) + cb];
+    const uint32_t n = b.boff[(size_t)p * (NB1_MAX + 1) + cb + 1] - B0;
+    __syncthreads();
+    finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true>(sm, b.fn + p, cb, B0, n, M, p, b, fo);
   }
 }
 

@@ -45,9 +45,9 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- optional per-kernel timing (bench.py's roofline block): CUDA events recorded on the
 // launching stream around every kernel while enabled.
-enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_HIST0, K_RADIX, K_RANKC, K_PREP,
+enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_FINISHB, K_HIST0, K_RADIX, K_RANKC, K_PREP,
                 K_MPART, K_FOLD, K_CHAIN, K_DECIDE, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_COUNT };
-const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_sample", "k_bhist", "k_bscan", "k_partition", "k_finish",
+const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_sample", "k_bhist", "k_bscan", "k_partition", "k_finish", "k_finish_big",
                                            "k_hist0", "k_radix_pass", "k_rank_codes", "k_param_prep",
                                            "k_merge_partition", "k_fold", "k_moments", "k_decide", "k_finalize",
                                            "k_summary", "k_compare", "k_checks", "k_synth"};
@@ -103,7 +103,7 @@ inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 // Workspace carve-up for one batch of PB parameters with M pooled draws each.
 struct Layout {
   size_t ztab, flag, header;  // shared part
-  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, spart, fallback, nfb, plist, hist, sel, sum, mean, sd, med, m0, apos,
+  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
       crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cwl0, cwl1, cnwl, per_batch;
   uint32_t ntiles, nchunks;
   void compute(int64_t PB, int64_t M, bool diag, int64_t C = 1, int64_t N = 1) {
@@ -127,6 +127,8 @@ struct Layout {
     spart = b; b += up((size_t)PB * nchunks * 2 * 8);
     fallback = b; b += up((size_t)PB);
     nfb = b; b += up(sizeof(int));
+    nbigb = b; b += up(sizeof(int));
+    biglist = b; b += up((size_t)PB * BIGLIST_PER_PARAM * 2 * 4);
     plist = b; b += up((size_t)PB * 4);
     hist = b; b += up((size_t)PB * 8 * 256 * 4);
     sel = b; b += up((size_t)PB * 4);
@@ -301,6 +303,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   static bool part_attr = false;
   if (!part_attr) {
     CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemSmall)));
+    CUDA_TRY(cudaFuncSetAttribute(k_finish_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemBig)));
     part_attr = true;
   }
 
@@ -322,6 +326,9 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     bb.spart = (double*)(wb + L.spart);
     bb.fallback = (uint8_t*)(wb + L.fallback);
     bb.nfb = (int*)(wb + L.nfb);
+    bb.nbigb = (int*)(wb + L.nbigb);
+    bb.biglist = (int*)(wb + L.biglist);
+    bb.biglist_cap = PB * BIGLIST_PER_PARAM;
     bb.plist = (int*)(wb + L.plist);
     bb.flag = flag;
     bb.pkey = (uint64_t*)(wb + L.pkey);
@@ -379,7 +386,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       CUDA_TRY(cudaEventRecord(ss.join, ss.s));
     }
     LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
-    LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1, PB), FIN_NT, 0, st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
+    LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
+    LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
     CUDA_TRY(cudaStreamWaitEvent(st, side_stream().join, 0));
 
     PrepOut po;
@@ -419,7 +427,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       cs.nwl = (int*)(wb + L.cnwl);
       CUDA_TRY(cudaMemsetAsync(cs.nwl, 0, 2 * sizeof(int), st));
       if (g.nunits)
-        LAUNCH(K_CHAIN, st, k_moments0<<<dim3((unsigned)(C * g.nunits), PB, 2), MO_NT, 0, st>>>(zz, g, cs.part));
+        LAUNCH(K_CHAIN, st, k_moments0<<<dim3((unsigned)(2 * C * g.nunits), PB), MO_NT, 0, st>>>(zz, g, cs.part));
       LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
       int cur = 0;
       for (uint32_t t0 = 1 + LAGB; t0 < (uint32_t)N; t0 += LAGB) {

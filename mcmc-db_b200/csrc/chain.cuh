@@ -107,13 +107,14 @@ __device__ __forceinline__ void lag_chunk(const double* __restrict__ ya, const d
 }
 
 // ---------------------------------------------------------------- round 0: lags 1..16 + moments
-// grid (C * nunits, PB, 2): blockIdx.z = kind.  The two sibling CTAs read the two halves of the
-// same 16-byte pairs, so DRAM sees each sector once.
+// grid (2 * C * nunits, PB): kind = blockIdx.x & 1.  The two sibling CTAs (adjacent block ids,
+// co-scheduled) read the two halves of the same 16-byte pairs, so DRAM sees each sector once.
 __global__ void __launch_bounds__(MO_NT, 4) k_moments0(const double2* __restrict__ zz, ChainGeom g, double* part) {
   __shared__ double y[MO_PAD];
   __shared__ double red[MO_NT / 32][MO_VALS];
-  const int p = blockIdx.y, kind = blockIdx.z;
-  const uint32_t c = blockIdx.x / g.nunits, u = blockIdx.x % g.nunits;
+  const int p = blockIdx.y, kind = blockIdx.x & 1;
+  const uint32_t cu = blockIdx.x >> 1;
+  const uint32_t c = cu / g.nunits, u = cu % g.nunits;
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   uint32_t a, b;
   unit_range(g, u, a, b);

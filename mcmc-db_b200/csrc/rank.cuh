@@ -334,17 +334,36 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
   // striped output: consecutive lanes -> consecutive merged positions, so the table and
   // (idx, kcode) reads are near-coalesced; only the final 16-byte scatter is random.
   const size_t pbase = (size_t)p * M;
-  for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) {
-    const uint32_t t = st[e];
-    const uint32_t k = any_tie ? sk[e] : 2u * (gbase + e) + 1u;
-    const uint32_t pos = idx[t];
-    const double zfv = b.ztab[k];
-    if (o.zz) {
-      o.zz[pbase + pos] = make_double2(b.ztab[kc[t]], zfv);
-    } else {
-      if (o.z) o.z[pbase + pos] = b.ztab[kc[t]];
-      if (o.zf) o.zf[pbase + pos] = zfv;
-      if (o.rankf) o.rankf[pbase + pos] = (double)(k + 1u) * 0.5;
+  // all gathers of the thread's 8 outputs are issued before any is used (memory-level parallelism)
+  uint32_t tt[RANK_IPT], kk[RANK_IPT], pos[RANK_IPT], kcv[RANK_IPT];
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    const uint32_t e = it * RANK_NT + threadIdx.x;
+    tt[it] = (e < n) ? st[e] : 0;
+    kk[it] = any_tie ? ((e < n) ? sk[e] : 1u) : 2u * (gbase + min(e, n - 1)) + 1u;
+  }
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    pos[it] = idx[tt[it]];
+    kcv[it] = kc[tt[it]];
+  }
+  double zb[RANK_IPT], zf[RANK_IPT];
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    zb[it] = b.ztab[kcv[it]];
+    zf[it] = b.ztab[kk[it]];
+  }
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    const uint32_t e = it * RANK_NT + threadIdx.x;
+    if (e < n) {
+      if (o.zz) {
+        o.zz[pbase + pos[it]] = make_double2(zb[it], zf[it]);
+      } else {
+        if (o.z) o.z[pbase + pos[it]] = zb[it];
+        if (o.zf) o.zf[pbase + pos[it]] = zf[it];
+        if (o.rankf) o.rankf[pbase + pos[it]] = (double)(kk[it] + 1u) * 0.5;
+      }
     }
   }
 }

@@ -442,6 +442,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
     uint16_t f[IPT];
 #pragma unroll
     for (int it = 0; it < IPT; ++it) {
+      if ((uint32_t)(it * NT) >= n) break;  // uniform: typical buckets fill 2-4 of the IPT slots
       const uint32_t e = it * NT + tid;
       if (e < n) {
         v[it] = key2dbl(pk[e]);
@@ -455,6 +456,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < IPT; ++it) {
+      if ((uint32_t)(it * NT) >= n) break;
       const uint32_t e = it * NT + tid;
       if (e < n) {
         const uint32_t slot = sm.foff[f[it]] + r[it];

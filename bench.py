@@ -105,7 +105,7 @@ def gpu_arm(args) -> None:
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from mcmc_ref_b200 import _native, batch
+    from mcmc_ref_b200 import _native, batch, sharding
 
     w = WORKLOADS[args.workload]
     P, C, N, MREF = w["P"], w["C"], w["N"], w["RC"] * w["RN"]
@@ -113,15 +113,13 @@ def gpu_arm(args) -> None:
     ref = batch.synth_fill(P, w["RC"], w["RN"], p0=rank * P, kind=1).reshape(P, MREF)
     ws = batch.Workspace()
     ws_cap = int(args.ws_gb * 2**30)
-    gathered = torch.empty((world * P, 16), dtype=torch.float64, device="cuda") if world > 1 else None
-    verdict = torch.ones(1, dtype=torch.int32, device="cuda")
 
     def step():
+        # this rank's parameter block, then the [P/G, 16] summary gather + verdict AND (NCCL)
         summary, passed = batch.full_pass(cand, ref, tolerance=TOL, workspace=ws, ws_cap_bytes=ws_cap)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, summary)
-            verdict.fill_(1 if passed else 0)
-            dist.all_reduce(verdict, op=dist.ReduceOp.MIN)
+            sharding.gather_summaries(summary, world * P)
+            passed = sharding.all_passed(passed, summary.device)
         return summary, passed
 
     def barrier():
@@ -202,9 +200,8 @@ def gpu_arm(args) -> None:
     def e2e_step():
         s, ok = batch.full_pass_host(cand_h, ref_h, tolerance=TOL, summary_host=sum_h, workspace=ws)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, s.cuda(non_blocking=True))
-            verdict.fill_(1 if ok else 0)
-            dist.all_reduce(verdict, op=dist.ReduceOp.MIN)
+            sharding.gather_summaries(s.cuda(non_blocking=True), world * P)
+            ok = sharding.all_passed(ok, torch.device("cuda", local))
         return s, ok
 
     e2e_step()

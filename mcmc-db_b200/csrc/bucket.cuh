@@ -491,7 +491,18 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
     const uint32_t a = sm.foff[fb], e = sm.foff[fb + 1];
     if (e - a > (uint32_t)BIG_FINE) continue;
     uint32_t less = 0, eq = 0, eqb = 0;
-    for (uint32_t t = a; t < e; ++t) {
+    // first 4 slots branch-free (covers almost every fine bucket), the rest in a loop
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const uint32_t t = a + d;
+      const bool in = t < e;
+      const double kt = sm.kd[in ? t : s];
+      less += (in && kt < k);
+      const bool same = in && (kt == k);
+      eq += same;
+      eqb += (same && t < s);
+    }
+    for (uint32_t t = a + 4; t < e; ++t) {
       const double kt = sm.kd[t];
       less += (kt < k);
       const bool same = (kt == k);

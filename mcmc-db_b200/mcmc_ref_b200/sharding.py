@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing: parameters are independent, so the path shards by parameter column.
+
+One process per GPU (torch.distributed; NCCL on GPUs, gloo in the CPU tests).  There is no
+data-path collective: each rank runs the full pass on its contiguous block of parameters;
+the only communication is one all_gather of the [P_local, 16] summary rows and one
+all_reduce(MIN) of the compare verdict.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_params: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block [lo, hi) of parameter columns owned by `rank` (sizes differ by at most 1)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank {rank} for world size {world}")
+    base, extra = divmod(n_params, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_summaries(local: torch.Tensor, n_params: int | None = None, group=None) -> torch.Tensor:
+    """All ranks receive the [P, K] summary of all parameters, in parameter order."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    k = local.shape[1]
+    if n_params is None:
+        counts = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        all_counts = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(all_counts, counts, group=group)
+        sizes = [int(c.item()) for c in all_counts]
+    else:
+        sizes = [hi - lo for lo, hi in (shard_bounds(n_params, world, r) for r in range(world))]
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} parameters, expected {sizes[rank]}")
+    if len(set(sizes)) == 1:
+        out = torch.empty((sum(sizes), k), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = max(sizes)
+    buf = torch.zeros((pad, k), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+def all_passed(local_ok: bool, device=None, group=None) -> bool:
+    """AND of the per-rank compare verdicts."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return bool(local_ok)
+    t = torch.tensor([1 if local_ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
+
+
+def full_pass_sharded(cand_local, ref_local, n_params: int | None = None, tolerance: float = 0.15, group=None,
+                      **kw) -> tuple[torch.Tensor, bool]:
+    """Full diagnostics + compare pass on this rank's parameter block, then the small gather."""
+    from . import batch
+
+    summary, ok = batch.full_pass(cand_local, ref_local, tolerance=tolerance, **kw)
+    return gather_summaries(summary, n_params, group), all_passed(ok, summary.device, group)

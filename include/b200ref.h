@@ -159,6 +159,18 @@ int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, in
                                double* summary_host /* [P][16] */, uint8_t* passed_host,
                                void* ws_dev, size_t ws_bytes);
 
+/* Batched log-density of the logistic-regression GLM (Stan: y ~ bernoulli_logit(X * beta)):
+ *   lp[s] = sum_n ( y[n] * eta - log(1 + exp(eta)) ),  eta = sum_d X[n][d] * beta[s][d]
+ * X [N][D], y [N] (0/1), beta [S][D] draws, lp [S]; all fp64 device pointers, row-major.
+ * EXTENSION: the reference packages the Stan text and data of such models (e.g.
+ * stan_models/wells_data-wells_dist.stan:9-11, provenance.py:539-606) but has no log-density
+ * code; parity is pinned against the fp64 oracle only (1e-6 relative).  The contraction runs
+ * on the tcgen05 tensor cores with split-bf16 operands and a fused likelihood epilogue. */
+size_t b200ref_glm_workspace_bytes(int64_t N, int64_t D, int64_t S);
+int b200ref_glm_logistic_lp_f64(const double* X_dev, const double* y_dev, const double* beta_dev,
+                                int64_t N, int64_t D, int64_t S, double* lp_dev,
+                                void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Synthetic workload of SURVEY.md 8(d) (bench/test utility, not on the hot path):
  * x[p][c][i] = mu_p + sigma_p * AR1(phi_p), counter-based on (seed, p0 + p, c, i)
  * so values do not depend on tiling or GPU count.  kind 0 = candidate [P][C][N],

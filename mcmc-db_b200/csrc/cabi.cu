@@ -16,6 +16,7 @@
 #include "bucket.cuh"
 #include "chain.cuh"
 #include "common.cuh"
+#include "glm.cuh"
 #include "rank.cuh"
 #include "sort.cuh"
 #include "synth.cuh"
@@ -46,11 +47,11 @@ int fail(int code, const char* fmt, ...) {
 // ---- optional per-kernel timing (bench.py's roofline block): CUDA events recorded on the
 // launching stream around every kernel while enabled.
 enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_FINISHB, K_HIST0, K_RADIX, K_RANKC, K_PREP,
-                K_MPART, K_FOLD, K_CHAIN, K_DECIDE, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_COUNT };
+                K_MPART, K_FOLD, K_CHAIN, K_DECIDE, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_GLM_PREP, K_GLM, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_sample", "k_bhist", "k_bscan", "k_partition", "k_finish", "k_finish_big",
                                            "k_hist0", "k_radix_pass", "k_rank_codes", "k_param_prep",
                                            "k_merge_partition", "k_fold", "k_moments", "k_decide", "k_finalize",
-                                           "k_summary", "k_compare", "k_checks", "k_synth"};
+                                           "k_summary", "k_compare", "k_checks", "k_synth", "k_glm_prep", "k_glm_logistic"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
@@ -720,6 +721,118 @@ int b200ref_synth_fill_f64(double* x, int64_t p0, int64_t P, int64_t C, int64_t 
   const unsigned blocks = (unsigned)((nchains + warps_per_block - 1) / warps_per_block);
   LAUNCH(K_SYNTH, (cudaStream_t)stream, k_synth<<<blocks, warps_per_block * 32, 0, (cudaStream_t)stream>>>(x, p0, P, C, N, seed, kind));
   CUDA_TRY(cudaGetLastError());
+  return B200REF_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// GLM log-density (logistic regression) on the tcgen05 tensor cores -- see csrc/glm.cuh
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// [rows][cols] bf16 row-major; box = 64 columns (128 B, one swizzle row) x box_rows rows
+int make_map_bf16(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(B200REF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GLM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200REF_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return B200REF_OK;
+}
+
+struct GlmLayout {
+  size_t bh, bl, xh, xl, yf, part, total;
+  int Dpad, n_row_tiles, n_draw_tiles, nsplit;
+  void compute(int64_t N, int64_t D, int64_t S) {
+    Dpad = (int)((D + GLM_BK - 1) / GLM_BK * GLM_BK);
+    n_row_tiles = (int)((N + GLM_BN - 1) / GLM_BN);
+    n_draw_tiles = (int)((S + GLM_BM - 1) / GLM_BM);
+    nsplit = std::max(1, std::min(std::min(8, n_row_tiles), (4 * 148 + n_draw_tiles - 1) / n_draw_tiles));
+    size_t o = 0;
+    bh = o; o += up((size_t)S * Dpad * 2);
+    bl = o; o += up((size_t)S * Dpad * 2);
+    xh = o; o += up((size_t)N * Dpad * 2);
+    xl = o; o += up((size_t)N * Dpad * 2);
+    yf = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
+    part = o; o += up((size_t)nsplit * S * 8);
+    total = o + 1024;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+size_t b200ref_glm_workspace_bytes(int64_t N, int64_t D, int64_t S) {
+  if (N < 1 || D < 1 || S < 1) return 0;
+  GlmLayout l;
+  l.compute(N, D, S);
+  return l.total;
+}
+
+int b200ref_glm_logistic_lp_f64(const double* X, const double* y, const double* beta, int64_t N, int64_t D, int64_t S,
+                                double* lp, void* ws, size_t ws_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!X || !y || !beta || !lp || N < 1 || D < 1 || S < 1) return fail(B200REF_ERR_ARG, "bad glm arguments");
+  if (D > 65536) return fail(B200REF_ERR_ARG, "D=%lld too large", (long long)D);
+  cudaStream_t st = (cudaStream_t)stream;
+  GlmLayout L;
+  L.compute(N, D, S);
+  if (!ws || ws_bytes < L.total) return fail(B200REF_ERR_WORKSPACE, "glm workspace needs %zu bytes", L.total);
+  char* w = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16 *bh = (__nv_bfloat16*)(w + L.bh), *bl = (__nv_bfloat16*)(w + L.bl);
+  __nv_bfloat16 *xh = (__nv_bfloat16*)(w + L.xh), *xl = (__nv_bfloat16*)(w + L.xl);
+  float* yf = (float*)(w + L.yf);
+  double* part = (double*)(w + L.part);
+  const int64_t nb = S * L.Dpad, nx = N * L.Dpad, npad = (int64_t)L.n_row_tiles * GLM_BN;
+  LAUNCH(K_GLM_PREP, st, k_glm_split<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(beta, S, (int)D, L.Dpad, bh, bl));
+  LAUNCH(K_GLM_PREP, st, k_glm_split<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(X, N, (int)D, L.Dpad, xh, xl));
+  LAUNCH(K_GLM_PREP, st, k_glm_y<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(y, N, npad, yf));
+  CUDA_TRY(cudaMemsetAsync(part, 0, (size_t)L.nsplit * S * 8, st));
+  CUtensorMap mbh, mbl, mxh, mxl;
+  int rc;
+  if ((rc = make_map_bf16(&mbh, bh, (uint64_t)S, (uint64_t)L.Dpad, GLM_BM))) return rc;
+  if ((rc = make_map_bf16(&mbl, bl, (uint64_t)S, (uint64_t)L.Dpad, GLM_BM))) return rc;
+  if ((rc = make_map_bf16(&mxh, xh, (uint64_t)N, (uint64_t)L.Dpad, GLM_BN))) return rc;
+  if ((rc = make_map_bf16(&mxl, xl, (uint64_t)N, (uint64_t)L.Dpad, GLM_BN))) return rc;
+  GlmParams prm;
+  prm.N = N; prm.S = S; prm.Dpad = L.Dpad;
+  prm.n_row_tiles = L.n_row_tiles; prm.n_draw_tiles = L.n_draw_tiles; prm.nsplit = L.nsplit;
+  prm.yf = yf; prm.lp_part = part;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(k_glm_logistic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));
+    attr = true;
+  }
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(nsm, L.n_draw_tiles * L.nsplit);
+  LAUNCH(K_GLM, st, k_glm_logistic<<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm));
+  LAUNCH(K_GLM_PREP, st, k_glm_reduce<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(part, L.nsplit, S, lp));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(st));
   return B200REF_OK;
 }
 

@@ -1,0 +1,310 @@
+// Batched GLM log-density: logistic regression  lp_s = sum_n [ y_n * eta_ns - log(1 + exp(eta_ns)) ],
+// eta = X beta_s  (Stan: y ~ bernoulli_logit(X * beta), e.g. packaged wells_data-wells_dist.stan:9-11).
+// The reference ships the Stan text and data of its posteriordb-style models but no
+// log-density code: this is an extension; parity is pinned only against
+// the fp64 numpy oracle (oracle/glm_oracle.py), tolerance 1e-6 relative.
+//
+// tcgen05 design (sm_100a):
+//   * the contraction eta[S x N] = beta[S x D] * X[N x D]^T runs on the 5th-gen tensor cores;
+//     fp64 inputs are split into bf16 hi + lo parts (16 significant bits) and three MMAs
+//     (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM -- |d eta| ~ 1e-5, which moves lp by
+//     < 1e-7 relative because the errors average out over the N terms;
+//   * UMMA tile 128 draws x 256 data rows x K 16, cta_group::1; DRAWS are the M dimension so
+//     that every TMEM lane (= one epilogue thread) owns one draw and can keep a private
+//     running sum over data rows -- no cross-thread reduction in the epilogue;
+//   * operands arrive by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 2-stage
+//     shared-memory ring (96 KB per stage: beta hi/lo 128x64, X hi/lo 256x64 bf16),
+//     full/empty mbarriers, one elected thread issues the MMAs, tcgen05.commit frees stages;
+//   * two 256-column accumulators (all 512 TMEM columns) ping-pong between the MMA warp and
+//     8 epilogue warps, which read eta with tcgen05.ld.32x32b.x32 and apply the fused
+//     likelihood y*eta - softplus(eta) in fp32 (ex2/lg2 MUFU), summing 32 columns in fp32 and
+//     then into an fp64 accumulator: the 26 GB eta matrix never exists in memory.
+//   * persistent CTAs; a work item = (draw tile, slice of the data rows); the <= NSPLIT partial
+//     sums per draw are combined by a tiny kernel in a fixed order.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace b200ref {
+
+constexpr int GLM_BM = 128;   // draws per tile   (UMMA M)
+constexpr int GLM_BN = 256;   // data rows per tile (UMMA N)
+constexpr int GLM_BK = 64;    // bf16 elements per k-block: 128 bytes = one swizzle row
+constexpr int GLM_STAGES = 2;
+constexpr int GLM_NT = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int GLM_EPI_WARP0 = 4;
+constexpr int GLM_EPI_THREADS = 256;
+constexpr uint32_t GLM_A_BYTES = GLM_BM * GLM_BK * 2;  // 16 KB
+constexpr uint32_t GLM_B_BYTES = GLM_BN * GLM_BK * 2;  // 32 KB
+constexpr uint32_t GLM_STAGE_BYTES = 2 * GLM_A_BYTES + 2 * GLM_B_BYTES;  // 96 KB
+constexpr size_t GLM_SMEM_BYTES = 1024 + (size_t)GLM_STAGES * GLM_STAGE_BYTES + 2 * GLM_BN * 4 + 256;
+
+struct GlmParams {
+  int64_t N, S;
+  int Dpad;            // multiple of 64
+  int n_row_tiles;     // ceil(N / 256)
+  int n_draw_tiles;    // ceil(S / 128)
+  int nsplit;          // row-tile slices per draw tile
+  const float* yf;     // [n_row_tiles * 256] y as float, padded with 0
+  double* lp_part;     // [nsplit][S], zero-initialised
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t_start = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u && clock64() - t_start > 4000000000ll) {  // ~2 s
+      printf("glm kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 256 x 16, bf16 in, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart):
+// start address >> 4 | LBO 1 | SBO 64 (1024 B >> 4) | version 1 (Blackwell) | layout SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)64 << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16: D fp32 (bits 4-5 = 1), A bf16 (bits 7-9 = 1), B bf16 (bits 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t GLM_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GLM_BN >> 3) << 17) |
+                               ((uint32_t)(GLM_BM >> 4) << 24);
+
+// ---- helper kernels -------------------------------------------------------------------------
+// fp64 [rows][D] -> bf16 hi, lo [rows][Dpad] (zero padded): x ~ hi + lo with 16 significant bits
+__global__ void k_glm_split(const double* __restrict__ src, int64_t rows, int D, int Dpad, __nv_bfloat16* __restrict__ hi,
+                            __nv_bfloat16* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Dpad) return;
+  const int64_t r = i / Dpad;
+  const int d = (int)(i % Dpad);
+  double x = (d < D) ? src[r * D + d] : 0.0;
+  const __nv_bfloat16 h = __double2bfloat16(x);
+  const double rem = x - (double)__bfloat162float(h);
+  hi[i] = h;
+  lo[i] = __double2bfloat16(rem);
+}
+__global__ void k_glm_y(const double* __restrict__ y, int64_t N, int64_t Npad, float* __restrict__ yf) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Npad) yf[i] = (i < N) ? (float)y[i] : 0.0f;
+}
+__global__ void k_glm_reduce(const double* __restrict__ part, int nsplit, int64_t S, double* __restrict__ lp) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double a = 0.0;
+  for (int h = 0; h < nsplit; ++h) a += part[(size_t)h * S + s];
+  lp[s] = a;
+}
+
+// ---- the fused GEMM + likelihood kernel -------------------------------------------------------
+__global__ void __launch_bounds__(GLM_NT, 1)
+k_glm_logistic(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+               const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, GlmParams prm) {
+  extern __shared__ unsigned char glm_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)glm_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1 KB
+  unsigned char* stage_base = smem;
+  float* ys = (float*)(smem + (size_t)GLM_STAGES * GLM_STAGE_BYTES);  // [2][256]
+  uint64_t* bars = (uint64_t*)(ys + 2 * GLM_BN);
+  uint64_t* full = bars;            // [2]  TMA -> MMA
+  uint64_t* empty = bars + 2;       // [2]  MMA -> TMA
+  uint64_t* tfull = bars + 4;       // [2]  MMA -> epilogue
+  uint64_t* tempty = bars + 6;      // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = prm.Dpad / GLM_BK;
+  const int tiles_per_split = (prm.n_row_tiles + prm.nsplit - 1) / prm.nsplit;
+  const int nitems = prm.n_draw_tiles * prm.nsplit;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < GLM_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], GLM_EPI_THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int dt = item / prm.nsplit, h = item % prm.nsplit;
+        const int t0 = h * tiles_per_split, t1 = min(t0 + tiles_per_split, prm.n_row_tiles);
+        for (int rt = t0; rt < t1; ++rt) {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* sb = stage_base + (size_t)stage * GLM_STAGE_BYTES;
+            mbar_expect_tx(&full[stage], GLM_STAGE_BYTES);
+            tma_load_2d(sb, &map_bh, &full[stage], kb * GLM_BK, dt * GLM_BM);
+            tma_load_2d(sb + GLM_A_BYTES, &map_bl, &full[stage], kb * GLM_BK, dt * GLM_BM);
+            tma_load_2d(sb + 2 * GLM_A_BYTES, &map_xh, &full[stage], kb * GLM_BK, rt * GLM_BN);
+            tma_load_2d(sb + 2 * GLM_A_BYTES + GLM_B_BYTES, &map_xl, &full[stage], kb * GLM_BK, rt * GLM_BN);
+            if (++stage == GLM_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      int stage = 0, abuf = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int h = item % prm.nsplit;
+        const int t0 = h * tiles_per_split, t1 = min(t0 + tiles_per_split, prm.n_row_tiles);
+        for (int rt = t0; rt < t1; ++rt) {
+          mbar_wait(&tempty[abuf], aphase ^ 1);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)abuf * GLM_BN;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(stage_base + (size_t)stage * GLM_STAGE_BYTES);
+            const uint64_t dah = umma_desc_k_sw128(sb), dal = umma_desc_k_sw128(sb + GLM_A_BYTES);
+            const uint64_t dbh = umma_desc_k_sw128(sb + 2 * GLM_A_BYTES);
+            const uint64_t dbl = umma_desc_k_sw128(sb + 2 * GLM_A_BYTES + GLM_B_BYTES);
+#pragma unroll
+            for (int k = 0; k < GLM_BK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 bytes = 2 x 16-byte units
+              tc_mma_bf16(tmem_d, dah + adv, dbh + adv, GLM_IDESC, (kb | k) ? 1u : 0u);
+              tc_mma_bf16(tmem_d, dah + adv, dbl + adv, GLM_IDESC, 1u);
+              tc_mma_bf16(tmem_d, dal + adv, dbh + adv, GLM_IDESC, 1u);
+            }
+            tc_commit(&empty[stage]);  // frees the smem stage once these MMAs retire
+            if (++stage == GLM_STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&tfull[abuf]);  // accumulator complete
+          if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= GLM_EPI_WARP0) {
+    // ================= epilogue: eta -> y*eta - softplus(eta), summed over data rows =================
+    const int ew = warp - GLM_EPI_WARP0;       // 0..7
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int chalf = ew >> 2;                 // which 128 columns
+    const int et = threadIdx.x - GLM_EPI_WARP0 * 32;  // 0..255
+    const int row = quad * 32 + lane;          // draw within the tile
+    int abuf = 0;
+    uint32_t aphase = 0;
+    const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int dt = item / prm.nsplit, h = item % prm.nsplit;
+      const int t0 = h * tiles_per_split, t1 = min(t0 + tiles_per_split, prm.n_row_tiles);
+      double acc = 0.0;
+      for (int rt = t0; rt < t1; ++rt) {
+        // stage y for this tile's 256 data rows (one element per epilogue thread)
+        ys[abuf * GLM_BN + et] = prm.yf[(size_t)rt * GLM_BN + et];
+        mbar_wait(&tfull[abuf], aphase);
+        tc_fence_after();
+        asm volatile("bar.sync 1, %0;" ::"n"(GLM_EPI_THREADS) : "memory");
+        const int64_t nvalid = prm.N - (int64_t)rt * GLM_BN;  // rows of this tile that exist
+        const float* yt = ys + abuf * GLM_BN;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col0 = chalf * 128 + cc * 32;
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(abuf * GLM_BN + col0), v);
+          float part = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float eta = __uint_as_float(v[j]);
+            const float a = fabsf(eta);
+            float e, l;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * LOG2E));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+            float term = yt[col0 + j] * eta - (fmaxf(eta, 0.0f) + l * LN2);
+            if (col0 + j >= nvalid) term = 0.0f;
+            part += term;
+          }
+          acc += (double)part;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[abuf]);
+        if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+      }
+      const int64_t s = (int64_t)dt * GLM_BM + row;
+      if (s < prm.S) atomicAdd(&prm.lp_part[(size_t)h * prm.S + s], acc);  // exactly two adds: order-free
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace b200ref

@@ -1,0 +1,31 @@
+"""Batched log-density of GLM-style posteriordb models over draws (extension: the reference
+packages the Stan text and data of these models but never evaluates them).
+
+``logistic_lp(X, y, beta)`` evaluates, for every draw ``beta[s]``,
+``sum_n y[n]*eta - log1p(exp(eta))`` with ``eta = X @ beta[s]`` -- the likelihood block of
+``y ~ bernoulli_logit(X * beta)`` -- on the tcgen05 tensor cores (csrc/glm.cuh).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _native, batch
+
+_WS = batch.Workspace()
+
+
+def logistic_lp(X, y, beta, workspace: batch.Workspace | None = None) -> torch.Tensor:
+    """lp[S] (float64, CUDA) for X [N, D], y [N] in {0, 1}, beta [S, D]."""
+    lib = _native.load()
+    xt, yt, bt = batch.to_device(X), batch.to_device(y).reshape(-1), batch.to_device(beta)
+    n, d = xt.shape
+    s = bt.shape[0]
+    if bt.shape[1] != d or yt.numel() != n:
+        raise ValueError(f"shape mismatch: X {tuple(xt.shape)}, y {tuple(yt.shape)}, beta {tuple(bt.shape)}")
+    lp = torch.empty(s, dtype=torch.float64, device=xt.device)
+    ws = (workspace or _WS).ensure(int(lib.b200ref_glm_workspace_bytes(n, d, s)))
+    _native.check(lib.b200ref_glm_logistic_lp_f64(xt.data_ptr(), yt.data_ptr(), bt.data_ptr(), n, d, s,
+                                                  lp.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  batch._stream_ptr()))
+    return lp

@@ -1,0 +1,66 @@
+"""GPU tests of the GLM log-density extension (tcgen05 kernel) against the fp64 oracle.
+
+Parity class: tolerance.  The reference has no log-density code, so the oracle is pinned
+only to the Stan semantics (oracle/glm_oracle.py); tolerance 1e-6 relative on lp
+(BASELINE.json north_star), the tests hold 2e-7.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import glm_oracle
+
+pytestmark = pytest.mark.gpu
+
+REL = 2e-7
+
+
+@pytest.fixture(scope="module")
+def LD():
+    import torch
+
+    assert torch.cuda.is_available()
+    import __graft_entry__ as g
+
+    g.build()
+    from mcmc_ref_b200 import logdensity
+
+    return logdensity
+
+
+def _problem(rng, n, d, s, spread=0.05):
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    beta_true = rng.standard_normal(d)
+    p = 1.0 / (1.0 + np.exp(-(X @ beta_true)))
+    y = (rng.random(n) < p).astype(np.float64)
+    beta = beta_true[None, :] + spread * rng.standard_normal((s, d))
+    return X, y, beta
+
+
+@pytest.mark.parametrize("shape", [(256, 64, 128), (1000, 100, 300), (5000, 256, 1000), (20000, 256, 4096),
+                                   (777, 3, 50), (3020, 2, 1000)])
+def test_logistic_lp_matches_oracle(LD, shape):
+    n, d, s = shape
+    rng = np.random.default_rng(n + d + s)
+    X, y, beta = _problem(rng, n, d, s)
+    got = LD.logistic_lp(X, y, beta).cpu().numpy()
+    want = glm_oracle.logistic_lp(X, y, beta)
+    rel = np.abs(got - want) / np.abs(want)
+    assert rel.max() < REL, (shape, rel.max(), got[:4], want[:4])
+
+
+def test_logistic_lp_large_eta_and_determinism(LD):
+    rng = np.random.default_rng(3)
+    X, y, beta = _problem(rng, 4096, 128, 512, spread=2.0)  # |eta| up to ~30: softplus saturates
+    a = LD.logistic_lp(X, y, beta).cpu().numpy()
+    b = LD.logistic_lp(X, y, beta).cpu().numpy()
+    assert np.array_equal(a, b)
+    want = glm_oracle.logistic_lp(X, y, beta)
+    assert (np.abs(a - want) / np.abs(want)).max() < REL
+
+
+def test_logistic_lp_shape_errors(LD):
+    with pytest.raises(ValueError, match="shape mismatch"):
+        LD.logistic_lp(np.zeros((10, 3)), np.zeros(10), np.zeros((4, 5)))

@@ -268,6 +268,84 @@ def gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
+def glm_arm(args) -> None:
+    """Config 3: logistic regression N=100k, D=256, batched log-density over 64k draws (tcgen05 path)."""
+    import numpy as np
+    import torch
+
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    from mcmc_ref_b200 import _native, batch, logdensity
+    from oracle import glm_oracle
+
+    n, d, s = args.glm_n, args.glm_d, args.glm_s
+    g = torch.Generator(device="cuda").manual_seed(4711)
+    X = torch.randn((n, d), dtype=torch.float64, device="cuda", generator=g) / d ** 0.5
+    beta_true = torch.randn(d, dtype=torch.float64, device="cuda", generator=g)
+    y = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) < torch.sigmoid(X @ beta_true)).double()
+    beta = beta_true[None, :] + 0.05 * torch.randn((s, d), dtype=torch.float64, device="cuda", generator=g)
+    ws = batch.Workspace()
+    for _ in range(max(args.warmup, 3)):
+        lp = logdensity.logistic_lp(X, y, beta, workspace=ws)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    l0 = _native.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        lp = logdensity.logistic_lp(X, y, beta, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _native.kernel_launches() - l0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    _native.profile(True)
+    _native.profile_read(reset=True)
+    for _ in range(args.steps):
+        logdensity.logistic_lp(X, y, beta, workspace=ws)
+    prof = _native.profile_read(reset=True)
+    _native.profile(False)
+    k_ms, k_n = prof["k_glm_logistic"]
+    flops = 2.0 * n * d * s
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    achieved = flops / (k_ms / max(k_n, 1) * 1e-3) / 1e12
+    # end to end: host fp64 buffers -> device -> lp back on the host
+    Xh, yh, bh = X.cpu().pin_memory(), y.cpu().pin_memory(), beta.cpu().pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lp_h = logdensity.logistic_lp(Xh.cuda(non_blocking=True), yh.cuda(non_blocking=True), bh.cuda(non_blocking=True),
+                                  workspace=ws).cpu()
+    e2e_s = time.perf_counter() - t0
+    # CPU baseline: fp64 numpy oracle (BLAS threads) on a sample of the draws + parity gate
+    ns = min(s, args.glm_cpu_draws)
+    idx = np.linspace(0, s - 1, ns).round().astype(int)
+    Xn, yn, bn = X.cpu().numpy(), y.cpu().numpy(), beta.cpu().numpy()[idx]
+    t0 = time.perf_counter()
+    want = glm_oracle.logistic_lp(Xn, yn, bn)
+    cpu_s = time.perf_counter() - t0
+    got = lp.cpu().numpy()[idx]
+    max_rel = float(np.max(np.abs(got - want) / np.abs(want)))
+    line = {
+        "metric": "glm log-density draws/s", "value": s / (ms * 1e-3), "unit": "draws/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2-split in, fp32 accumulate, fp64 sum", "data": "synthetic",
+        "config": {"workload": f"c3: logistic regression N={n}, D={d}, batched log-density over {s} draws",
+                   "l2": f"operands {(n + s) * d * 4 / 1e6:.0f} MB of bf16 hi/lo re-streamed per tile, larger than L2"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": s / e2e_s, "unit": "draws/s", "h2d_bytes_per_step": 8 * (n * d + n + s * d),
+                "d2h_bytes_per_step": 8 * s, "steps": 1},
+        "roofline": {"bound": "tensor", "kernel": "k_glm_logistic", "achieved": round(achieved, 1), "peak": peak,
+                     "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "note": "algorithmic flops 2*N*D*S; the kernel issues 3 bf16 MMAs per product for fp64-class accuracy",
+                     "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}},
+        "cpu_baseline": {"value": ns / cpu_s, "unit": "draws/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{ns} of {s} draws, numpy fp64 oracle (BLAS threads), {cpu_s:.1f} s"},
+        "parity": {"draws_checked": int(ns), "max_rel_err": max_rel, "ok": bool(max_rel < 1e-6)},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def reference_arm(args) -> None:
     """The reference algorithm on the host cores (oracle port; the Python reference itself
     cannot travel to the GPU box).  Rank 0 only; other ranks exit without work."""
@@ -311,14 +389,20 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3"])
+    ap.add_argument("--glm-n", type=int, default=100_000)
+    ap.add_argument("--glm-d", type=int, default=256)
+    ap.add_argument("--glm-s", type=int, default=65_536)
+    ap.add_argument("--glm-cpu-draws", type=int, default=512)
     ap.add_argument("--ws-gb", type=float, default=16.0, help="cap of the device workspace")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-params-per-core", type=int, default=24)
     ap.add_argument("--ref-params-per-core", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "c3":
+        glm_arm(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)

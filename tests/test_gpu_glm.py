@@ -2,7 +2,8 @@
 
 Parity class: tolerance.  The reference has no log-density code, so the oracle is pinned
 only to the Stan semantics (oracle/glm_oracle.py); tolerance 1e-6 relative on lp
-(BASELINE.json north_star), the tests hold 2e-7.
+(BASELINE.json north_star).  Error model: the split-bf16 contraction leaves |d eta| ~ 1e-5 per
+element, so |d lp| ~ 0.5e-5 * sqrt(N): 6e-7 relative at N = 256, 3e-8 at N = 100k.
 """
 
 from __future__ import annotations
@@ -14,7 +15,7 @@ from oracle import glm_oracle
 
 pytestmark = pytest.mark.gpu
 
-REL = 2e-7
+REL = 1e-6
 
 
 @pytest.fixture(scope="module")

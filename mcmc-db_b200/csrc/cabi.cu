@@ -375,16 +375,19 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     rb.ztab = ztab;
     const dim3 gt(L.ntiles, PB);
     {
+      // while per-kernel timing is on, the fallback runs on the main stream so that every
+      // event pair brackets one kernel alone (overlapped launches would share their interval)
       SideStream& ss = side_stream();
+      cudaStream_t fs = g_prof ? st : ss.s;
       CUDA_TRY(cudaEventRecord(ss.fork, st));
-      CUDA_TRY(cudaStreamWaitEvent(ss.s, ss.fork, 0));
+      CUDA_TRY(cudaStreamWaitEvent(fs, ss.fork, 0));
       const int fbg = std::min(PB, FALLBACK_GRID);
-      LAUNCH(K_HIST0, ss.s, k_hist0<<<fbg, 1024, 0, ss.s>>>(xb, (uint32_t)M, sb));
-      LAUNCH(K_RADIX, ss.s, k_radix_pass<true><<<fbg, SORT_NT, 0, ss.s>>>(xb, (uint32_t)M, 0, sb));
+      LAUNCH(K_HIST0, fs, k_hist0<<<fbg, 1024, 0, fs>>>(xb, (uint32_t)M, sb));
+      LAUNCH(K_RADIX, fs, k_radix_pass<true><<<fbg, SORT_NT, 0, fs>>>(xb, (uint32_t)M, 0, sb));
       for (int pass = 1; pass < 8; ++pass)
-        LAUNCH(K_RADIX, ss.s, k_radix_pass<false><<<fbg, SORT_NT, 0, ss.s>>>(xb, (uint32_t)M, pass, sb));
-      LAUNCH(K_RANKC, ss.s, k_rank_codes<<<dim3(L.ntiles, std::min(PB, 8)), RANK_NT, 0, ss.s>>>(rb, (uint32_t)M, rank_b_batch));
-      CUDA_TRY(cudaEventRecord(ss.join, ss.s));
+        LAUNCH(K_RADIX, fs, k_radix_pass<false><<<fbg, SORT_NT, 0, fs>>>(xb, (uint32_t)M, pass, sb));
+      LAUNCH(K_RANKC, fs, k_rank_codes<<<dim3(L.ntiles, std::min(PB, 8)), RANK_NT, 0, fs>>>(rb, (uint32_t)M, rank_b_batch));
+      CUDA_TRY(cudaEventRecord(ss.join, fs));
     }
     LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
     LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
@@ -646,7 +649,11 @@ int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, in
   CUDA_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
   // split: 2 input slabs + a compute workspace sized for one slab
-  int64_t slab = std::min<int64_t>(P, 1024);
+  // slab size: ~1/16 of the input, between 32 MB and 256 MB of draws, so the PCIe copy of one
+  // slab hides the kernels of the previous one and the exposed tail is one slab's compute
+  const size_t total_in = per_param_in * (size_t)P;
+  const size_t slab_bytes = std::min<size_t>(std::max<size_t>(total_in / 16, (size_t)32 << 20), (size_t)256 << 20);
+  int64_t slab = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t)(slab_bytes / per_param_in)));
   size_t need = 0;
   for (; slab >= 1; slab = (slab > 1) ? slab / 2 : 0) {
     need = 2 * up(per_param_in * slab) + b200ref_workspace_bytes(slab, C, N) + fused_tail_bytes(slab) + ALIGN;

@@ -2,7 +2,7 @@
 // eta = X beta_s  (Stan: y ~ bernoulli_logit(X * beta), e.g. packaged wells_data-wells_dist.stan:9-11).
 // The reference ships the Stan text and data of its posteriordb-style models but no
 // log-density code: this is an extension; parity is pinned only against
-// the fp64 numpy oracle (oracle/glm_oracle.py), tolerance 1e-6 relative.
+// an fp64 numpy restatement of the Stan likelihood kept with the tests, tolerance 1e-6 relative.
 //
 // tcgen05 design (sm_100a):
 //   * the contraction eta[S x N] = beta[S x D] * X[N x D]^T runs on the 5th-gen tensor cores;

@@ -146,7 +146,7 @@ struct Layout {
       const ChainGeom g = chain_geom(C, N);
       const size_t units = (size_t)C * g.nunits;
       cpart = b; b += up((size_t)PB * units * 2 * MO_VALS * 8);
-      cpartr = b; b += up((size_t)2 * PB * units * LAGB * 8);
+      cpartr = b; b += up((size_t)2 * PB * units * LAGR * 8);
       cmean = b; b += up((size_t)2 * PB * C * 8);
       csum = b; b += up((size_t)2 * PB * C * 8);
       chead = b; b += up((size_t)2 * PB * C * 8);
@@ -306,6 +306,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
     CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemSmall)));
     CUDA_TRY(cudaFuncSetAttribute(k_finish_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemBig)));
+    CUDA_TRY(cudaFuncSetAttribute(k_moments0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Mo0Smem)));
+    CUDA_TRY(cudaFuncSetAttribute(k_moments_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoRSmem)));
     part_attr = true;
   }
 
@@ -431,16 +433,16 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       cs.nwl = (int*)(wb + L.cnwl);
       CUDA_TRY(cudaMemsetAsync(cs.nwl, 0, 2 * sizeof(int), st));
       if (g.nunits)
-        LAUNCH(K_CHAIN, st, k_moments0<<<dim3((unsigned)(2 * C * g.nunits), PB), MO_NT, 0, st>>>(zz, g, cs.part));
+        LAUNCH(K_CHAIN, st, k_moments0<<<dim3((unsigned)(C * g.nunits), PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, cs.part));
       LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
       int cur = 0;
-      for (uint32_t t0 = 1 + LAGB; t0 < (uint32_t)N; t0 += LAGB) {
+      for (uint32_t t0 = 1 + LAGB; t0 < (uint32_t)N; t0 += LAGR) {
         int nwork = 0;
         CUDA_TRY(cudaMemcpyAsync(&nwork, cs.nwl + cur, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         if (nwork == 0) break;
         CUDA_TRY(cudaMemsetAsync(cs.nwl + (cur ^ 1), 0, sizeof(int), st));
-        LAUNCH(K_CHAIN, st, k_moments_r<<<dim3((unsigned)(C * g.nunits), nwork), MO_NT, 0, st>>>(zz, g, t0, cs.wl[cur], cs.partr));
+        LAUNCH(K_CHAIN, st, k_moments_r<<<dim3((unsigned)(C * g.nunits), nwork), MO_CTA, sizeof(MoRSmem), st>>>(zz, g, t0, cs.wl[cur], cs.partr));
         LAUNCH(K_DECIDE, st, k_decide_r<<<nwork, DEC_NT, 0, st>>>(zz, g, PB, t0, cur, cs));
         cur ^= 1;
       }

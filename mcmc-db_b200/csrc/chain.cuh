@@ -25,16 +25,21 @@
 
 namespace b200ref {
 
-constexpr int MO_NT = 128;
-constexpr int LAGB = 16;                 // lags per round
+constexpr int MO_NT = 128;               // threads working on one kind / one lag block
+constexpr int MO_CTA = 2 * MO_NT;        // threads per moments CTA
+constexpr int LAGB = 16;                 // lags per thread block half; round 0 covers lags 1..16
+constexpr int LAGR = 2 * LAGB;           // lags per later round (the two CTA halves take 16 each)
 constexpr int CHUNK = 16;                // consecutive draws per thread step
 constexpr int MO_SUB = MO_NT * CHUNK;    // 2048 draws per sub-tile
-constexpr int MO_SEGMAX = 4 * MO_SUB;    // a unit covers at most 8192 draws
-constexpr int MO_VALS = LAGB + 4;        // per (unit, kind) in round 0: 16 lag sums + {sum, sq, min, max}
+constexpr int MO_UNIT_TILES = 4;        // a unit (one CTA) covers at most 4 sub-tiles = 8192 draws
+constexpr int MO_VALS = LAGB + 10;       // per (unit, kind) in round 0: 16 lag sums + 2 x {sum, sq, first, differs, present}
 constexpr int DEC_NT = 64;
 
+// Chains are cut into units of whole 2048-draw sub-tiles, independent of the split point: the lag
+// products run over the unsplit chain (diagnostics.py:55-56), only sum / sum of squares are kept
+// per half (split R-hat, diagnostics.py:76-85).
 struct ChainGeom {
-  uint32_t C, N, half, nseg, seglen, nunits;  // nunits = 2 * nseg units per chain
+  uint32_t C, N, half, ntiles, tpu, nunits;  // tpu = sub-tiles per unit
 };
 
 __host__ inline ChainGeom chain_geom(int64_t C, int64_t N) {
@@ -42,21 +47,27 @@ __host__ inline ChainGeom chain_geom(int64_t C, int64_t N) {
   g.C = (uint32_t)C;
   g.N = (uint32_t)N;
   g.half = g.N / 2;
-  g.nseg = g.half ? (g.half + MO_SEGMAX - 1) / MO_SEGMAX : 0;
-  g.seglen = g.nseg ? (((g.half + g.nseg - 1) / g.nseg + CHUNK - 1) / CHUNK) * CHUNK : 0;
-  g.nunits = 2 * g.nseg;
+  g.ntiles = (g.N + MO_SUB - 1) / MO_SUB;
+  const uint32_t nu = (g.ntiles + MO_UNIT_TILES - 1) / MO_UNIT_TILES;
+  g.tpu = (g.ntiles + nu - 1) / nu;
+  g.nunits = (g.ntiles + g.tpu - 1) / g.tpu;
   return g;
 }
 
 __device__ __forceinline__ void unit_range(const ChainGeom& g, uint32_t u, uint32_t& a, uint32_t& b) {
-  const uint32_t h = u / g.nseg, s = u % g.nseg;
-  a = h * g.half + s * g.seglen;
-  b = min(h * g.half + (s + 1) * g.seglen, (h + 1) * g.half);
-  if (a > b) a = b;
+  a = min(g.N, u * g.tpu * (uint32_t)MO_SUB);
+  b = min(g.N, (u + 1) * g.tpu * (uint32_t)MO_SUB);
 }
 
-__host__ __device__ __forceinline__ uint32_t pad_idx(uint32_t e) { return e + (e >> 4); }
-constexpr int MO_PAD = MO_SUB + 2 * LAGB + (MO_SUB + 2 * LAGB) / 16 + 2;
+// Shared-memory tiles hold 16-draw groups padded to 18 doubles: a thread's 16 consecutive draws
+// start 144 B apart, so its 16-byte LDS.128 reads are bank-conflict free and stay 16-byte aligned.
+__host__ __device__ __forceinline__ uint32_t pad_idx(uint32_t e) { return e + 2u * (e >> 4); }
+constexpr int MO_HALO0 = LAGB;                      // round 0 reads 16 draws past the sub-tile
+constexpr int MO_HALOR = LAGR;                      // later rounds: 32 (second half's window)
+constexpr int MO_RAW0 = MO_SUB + MO_HALO0;          // double2 pairs staged per sub-tile by TMA
+constexpr int MO_RAWR = MO_SUB + MO_HALOR;
+constexpr int MO_PAD0 = (MO_RAW0 / CHUNK + 1) * (CHUNK + 2);
+constexpr int MO_PADR = (MO_RAWR / CHUNK + 1) * (CHUNK + 2);
 
 // v[16] per lane -> lane l returns the warp total of v[l & 15]  (16 shuffles)
 __device__ __forceinline__ double warp_reduce_16(double (&v)[16]) {
@@ -77,7 +88,7 @@ __device__ __forceinline__ double warp_reduce_16(double (&v)[16]) {
 
 struct ChainState {
   double* part;      // [PB][C*nunits][2][MO_VALS] round-0 partial sums
-  double* partr;     // [nwork][C*nunits][LAGB]   later rounds
+  double* partr;     // [nwork][C*nunits][LAGR]   later rounds
   double* cmean;     // [2*PB][C]  unsplit chain means
   double* csum;      // [2*PB][C]  chain totals
   double* head;      // [2*PB][C]  sum of the first (t0 - 1) draws of the chain
@@ -91,125 +102,248 @@ struct ChainState {
   int64_t* lag;      // [2][PB] first lag with rho < 0 (N if none)
 };
 
-// acc[l] += sum_s ya[i0 + s] * yw[i0 + s + l + woff]   (s < nvalid; yw zero beyond the chain)
-__device__ __forceinline__ void lag_chunk(const double* __restrict__ ya, const double* __restrict__ yw, uint32_t woff,
-                                          uint32_t i0, uint32_t nvalid, double* __restrict__ acc) {
-  double w[LAGB + CHUNK - 1];
+// 16 consecutive doubles of a padded tile starting at group base gb (16-byte aligned) -> registers
+__device__ __forceinline__ void load16(const double* __restrict__ gb, double* __restrict__ u) {
 #pragma unroll
-  for (int l = 0; l < LAGB - 1; ++l) w[l] = yw[pad_idx(i0 + woff + l)];
-#pragma unroll
-  for (int s = 0; s < CHUNK; ++s) {
-    w[s + LAGB - 1] = yw[pad_idx(i0 + woff + s + LAGB - 1)];
-    const double a = ((uint32_t)s < nvalid) ? ya[pad_idx(i0 + s)] : 0.0;
-#pragma unroll
-    for (int l = 0; l < LAGB; ++l) acc[l] = fma(a, w[s + l], acc[l]);
+  for (int k = 0; k < 8; ++k) {
+    const double2 t = *reinterpret_cast<const double2*>(gb + 2 * k);
+    u[2 * k] = t.x;
+    u[2 * k + 1] = t.y;
   }
 }
 
+// One elected thread: TMA bulk copy of `npairs` {z_bulk, z_folded} pairs into the staging buffer.
+__device__ __forceinline__ void stage_pairs(double2* raw, const double2* src, uint32_t npairs, uint64_t* bar) {
+  fence_proxy_async();  // earlier generic reads of `raw` are ordered before the async-proxy writes
+  mbar_expect_tx(bar, npairs * 16u);
+  bulk_g2s(raw, src, npairs * 16u, bar);
+}
+
 // ---------------------------------------------------------------- round 0: lags 1..16 + moments
-// grid (2 * C * nunits, PB): kind = blockIdx.x & 1.  The two sibling CTAs (adjacent block ids,
-// co-scheduled) read the two halves of the same 16-byte pairs, so DRAM sees each sector once.
-__global__ void __launch_bounds__(MO_NT, 4) k_moments0(const double2* __restrict__ zz, ChainGeom g, double* part) {
-  __shared__ double y[MO_PAD];
-  __shared__ double red[MO_NT / 32][MO_VALS];
-  const int p = blockIdx.y, kind = blockIdx.x & 1;
-  const uint32_t cu = blockIdx.x >> 1;
-  const uint32_t c = cu / g.nunits, u = cu % g.nunits;
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+// grid (C * nunits, PB), 256 threads: one CTA streams one unit of one chain for BOTH kinds.  Each
+// sub-tile of 2048 + 16 pairs arrives by one TMA bulk copy (UBLKCP) into a staging buffer and is
+// split into two padded fp64 tiles (double-buffered: one barrier per sub-tile); the next copy is in
+// flight while warps 0-3 accumulate z_bulk and warps 4-7 z_folded: 16 raw lag products
+// R_t = sum_i y_i y_{i+t}, and per half of the chain the sum, the sum of squares and "some draw
+// differs from the first" (a constant half must give variance 0 exactly).
+struct Mo0Smem {
+  double2 raw[MO_RAW0];
+  double y[2][2][MO_PAD0];  // [buffer][kind]
+  double red[2][MO_NT / 32][MO_VALS];
+  uint64_t bar;
+};
+
+__global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restrict__ zz, ChainGeom g, double* part) {
+  extern __shared__ __align__(128) unsigned char mo_smem_raw[];
+  Mo0Smem& S = *reinterpret_cast<Mo0Smem*>(mo_smem_raw);
+  const int p = blockIdx.y;
+  const uint32_t c = blockIdx.x / g.nunits, u = blockIdx.x % g.nunits;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int kind = tid >> 7, ct = tid & (MO_NT - 1), wp = ct >> 5;
   uint32_t a, b;
   unit_range(g, u, a, b);
-  const double* zc = reinterpret_cast<const double*>(zz + ((size_t)p * g.C + c) * g.N) + kind;
-  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
+  if (tid == 0) {
+    mbar_init(&S.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0 && a < b) stage_pairs(S.raw, zc + a, min((uint32_t)MO_RAW0, g.N - a), &S.bar);
+  const uint32_t half = g.half, two = 2 * g.half;
+  // first draw of this unit in each half (if any)
+  const bool has1 = a < half, has2 = b > half && max(a, half) < two;
+  double f1 = 0.0, f2 = 0.0;
+  if (has1) { const double2 f = zc[a]; f1 = kind ? f.y : f.x; }
+  if (has2) { const double2 f = zc[max(a, half)]; f2 = kind ? f.y : f.x; }
   double acc[LAGB];
 #pragma unroll
   for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
-  double sm = 0.0, sq = 0.0, mn = inf, mx = -inf;
-  for (uint32_t sub = a; sub < b; sub += MO_SUB) {
+  double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0;
+  bool d1 = false, d2 = false;
+  uint32_t phase = 0, buf = 0;
+  for (uint32_t sub = a; sub < b; sub += MO_SUB, buf ^= 1u) {
     const uint32_t len = min((uint32_t)MO_SUB, b - sub);
-    __syncthreads();
-    for (uint32_t i = tid; i < MO_SUB + 2 * LAGB; i += MO_NT) {
-      const uint32_t gi = sub + i;
-      y[pad_idx(i)] = (gi < g.N) ? zc[2 * (size_t)gi] : 0.0;
+    const uint32_t nel = min((uint32_t)MO_RAW0, g.N - sub);  // pairs the copy delivered; the rest reads as 0
+    mbar_wait(&S.bar, phase);
+    phase ^= 1u;
+    double* y0 = S.y[buf][0];
+    double* y1 = S.y[buf][1];
+#pragma unroll
+    for (int it = 0; it < MO_SUB / MO_CTA; ++it) {
+      const uint32_t i = it * MO_CTA + tid;
+      const double2 v = (i < nel) ? S.raw[i] : make_double2(0.0, 0.0);
+      y0[pad_idx(i)] = v.x;
+      y1[pad_idx(i)] = v.y;
     }
-    __syncthreads();
-    const uint32_t i0 = tid * CHUNK;
+    if (tid < MO_HALO0) {
+      const uint32_t i = MO_SUB + tid;
+      const double2 v = (i < nel) ? S.raw[i] : make_double2(0.0, 0.0);
+      y0[pad_idx(i)] = v.x;
+      y1[pad_idx(i)] = v.y;
+    }
+    __syncthreads();  // tiles complete, staging buffer free; buffer buf^1 was last read before this barrier
+    if (tid == 0 && sub + MO_SUB < b)
+      stage_pairs(S.raw, zc + sub + MO_SUB, min((uint32_t)MO_RAW0, g.N - (sub + MO_SUB)), &S.bar);
+    const uint32_t i0 = ct * CHUNK;
     if (i0 < len) {
       const uint32_t nvalid = min((uint32_t)CHUNK, len - i0);
-      lag_chunk(y, y, 1, i0, nvalid, acc);
+      const uint32_t g0 = sub + i0;
+      double w[2 * CHUNK];
+      const double* gb = &S.y[buf][kind][ct * (CHUNK + 2)];
+      load16(gb, w);
+      load16(gb + CHUNK + 2, w + CHUNK);
+      const bool in1 = g0 + CHUNK <= half, in2 = g0 >= half && g0 + CHUNK <= two;
+      if (nvalid == CHUNK && (in1 || in2)) {
+        const double fr = in1 ? f1 : f2;
+        double ls = 0.0, lq = 0.0;
+        bool ld = false;
 #pragma unroll
-      for (int s = 0; s < CHUNK; ++s) {
-        if ((uint32_t)s < nvalid) {
-          const double v = y[pad_idx(i0 + s)];
-          sm += v; sq = fma(v, v, sq); mn = fmin(mn, v); mx = fmax(mx, v);
+        for (int s = 0; s < CHUNK; ++s) {
+          const double v = w[s];
+          ls += v;
+          lq = fma(v, v, lq);
+          ld |= (v != fr);
+#pragma unroll
+          for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + 1 + l], acc[l]);
+        }
+        if (in1) { s1 += ls; q1 += lq; d1 |= ld; } else { s2 += ls; q2 += lq; d2 |= ld; }
+      } else {
+#pragma unroll
+        for (int s = 0; s < CHUNK; ++s) {
+          const bool ok = (uint32_t)s < nvalid;
+          const double v = ok ? w[s] : 0.0;
+          const uint32_t gi = g0 + s;
+          if (ok && gi < half) { s1 += v; q1 = fma(v, v, q1); d1 |= (v != f1); }
+          else if (ok && gi < two) { s2 += v; q2 = fma(v, v, q2); d2 |= (v != f2); }
+#pragma unroll
+          for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + 1 + l], acc[l]);
         }
       }
     }
   }
-  // unit totals: 16 lag sums by the halving reduce, 4 statistics by butterflies
+  // unit totals: 16 lag sums by the halving reduce, the half statistics by butterflies
   const double tot = warp_reduce_16(*reinterpret_cast<double (*)[16]>(acc));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    sm += __shfl_xor_sync(FULL, sm, o); sq += __shfl_xor_sync(FULL, sq, o);
-    mn = fmin(mn, __shfl_xor_sync(FULL, mn, o)); mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    s1 += __shfl_xor_sync(FULL, s1, o);
+    q1 += __shfl_xor_sync(FULL, q1, o);
+    s2 += __shfl_xor_sync(FULL, s2, o);
+    q2 += __shfl_xor_sync(FULL, q2, o);
+  }
+  const bool w1 = __any_sync(FULL, d1), w2 = __any_sync(FULL, d2);
+  double* r = S.red[kind][wp];
+  if (lane < LAGB) r[lane] = tot;
+  if (lane == 0) {
+    r[16] = s1; r[17] = q1; r[18] = f1; r[19] = w1 ? 1.0 : 0.0; r[20] = has1 ? 1.0 : 0.0;
+    r[21] = s2; r[22] = q2; r[23] = f2; r[24] = w2 ? 1.0 : 0.0; r[25] = has2 ? 1.0 : 0.0;
   }
   __syncthreads();
-  if (lane < LAGB) red[wp][lane] = tot;
-  if (lane == 0) { red[wp][16] = sm; red[wp][17] = sq; red[wp][18] = mn; red[wp][19] = mx; }
-  __syncthreads();
-  if (tid < MO_VALS) {
-    double v = red[0][tid];
+  if (ct < MO_VALS) {
+    double v = S.red[kind][0][ct];
+    const bool copy = (ct == 18 || ct == 20 || ct == 23 || ct == 25);  // first values / presence: not summed
+    if (!copy) {
 #pragma unroll
-    for (int k = 1; k < MO_NT / 32; ++k) {
-      const double o = red[k][tid];
-      v = (tid < 18) ? v + o : (tid == 18 ? fmin(v, o) : fmax(v, o));
+      for (int k = 1; k < MO_NT / 32; ++k) v += S.red[kind][k][ct];
     }
-    part[((((size_t)p * g.C + c) * g.nunits + u) * 2 + kind) * MO_VALS + tid] = v;
+    part[((((size_t)p * g.C + c) * g.nunits + u) * 2 + kind) * MO_VALS + ct] = v;
   }
 }
 
-// ---------------------------------------------------------------- later rounds: one kind, lags t0 .. t0+15
-__global__ void __launch_bounds__(MO_NT, 4) k_moments_r(const double2* __restrict__ zz, ChainGeom g, uint32_t t0,
-                                                     const int* __restrict__ wl, double* partr) {
-  __shared__ double ya[MO_PAD], yw[MO_PAD];
-  __shared__ double red[MO_NT / 32][LAGB];
+// ---------------------------------------------------------------- later rounds: one kind, lags t0 .. t0+31
+// grid (C * nunits, nwork), 256 threads.  Two TMA-staged tiles per sub-tile: first factors y[i] and
+// second factors y[i + t0 + ...]; threads 0-127 accumulate lags t0..t0+15, threads 128-255 lags
+// t0+16..t0+31 over the same draws, so one pass over a sticky chain advances 32 lags.
+struct MoRSmem {
+  double2 rawa[MO_RAW0];
+  double2 raww[MO_RAWR];
+  double ya[MO_PAD0];
+  double yw[MO_PADR];
+  double red[2][MO_NT / 32][LAGB];
+  uint64_t bar;
+};
+
+__global__ void __launch_bounds__(MO_CTA, 2) k_moments_r(const double2* __restrict__ zz, ChainGeom g, uint32_t t0,
+                                                         const int* __restrict__ wl, double* partr) {
+  extern __shared__ __align__(128) unsigned char mo_smem_raw[];
+  MoRSmem& S = *reinterpret_cast<MoRSmem*>(mo_smem_raw);
   const int item = wl[blockIdx.y];
   const int p = item >> 1, kind = item & 1;
   const uint32_t c = blockIdx.x / g.nunits, u = blockIdx.x % g.nunits;
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int hb = tid >> 7, ct = tid & (MO_NT - 1), wp = ct >> 5;  // hb: which block of 16 lags
   uint32_t a, b;
   unit_range(g, u, a, b);
   const uint32_t lim = (g.N > t0) ? g.N - t0 : 0;  // first factors need i + t0 < N
   b = min(b, lim);
-  const double* zc = reinterpret_cast<const double*>(zz + ((size_t)p * g.C + c) * g.N) + kind;
+  const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
+  if (tid == 0) {
+    mbar_init(&S.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto stage = [&](uint32_t sub) {  // sub < lim, so both copies are non-empty
+    fence_proxy_async();
+    const uint32_t na = min((uint32_t)MO_RAW0, g.N - sub), nw = min((uint32_t)MO_RAWR, g.N - (sub + t0));
+    mbar_expect_tx(&S.bar, (na + nw) * 16u);
+    bulk_g2s(S.rawa, zc + sub, na * 16u, &S.bar);
+    bulk_g2s(S.raww, zc + sub + t0, nw * 16u, &S.bar);
+  };
   double acc[LAGB];
 #pragma unroll
   for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
+  if (a < b && tid == 0) stage(a);
+  uint32_t phase = 0;
   for (uint32_t sub = a; sub < b; sub += MO_SUB) {
     const uint32_t len = min((uint32_t)MO_SUB, b - sub);
-    __syncthreads();
-    for (uint32_t i = tid; i < MO_SUB + 2 * LAGB; i += MO_NT) {
-      const uint32_t ga = sub + i, gw = sub + t0 + i;
-      ya[pad_idx(i)] = (ga < g.N) ? zc[2 * (size_t)ga] : 0.0;
-      yw[pad_idx(i)] = (gw < g.N) ? zc[2 * (size_t)gw] : 0.0;
+    const uint32_t na = min((uint32_t)MO_RAW0, g.N - sub), nw = min((uint32_t)MO_RAWR, g.N - (sub + t0));
+    mbar_wait(&S.bar, phase);
+    phase ^= 1u;
+    {
+      const double* ra = reinterpret_cast<const double*>(S.rawa) + kind;
+      const double* rw = reinterpret_cast<const double*>(S.raww) + kind;
+#pragma unroll
+      for (int it = 0; it < MO_SUB / MO_CTA; ++it) {
+        const uint32_t i = it * MO_CTA + tid;
+        S.ya[pad_idx(i)] = (i < na) ? ra[2 * i] : 0.0;
+        S.yw[pad_idx(i)] = (i < nw) ? rw[2 * i] : 0.0;
+      }
+      if (tid < MO_HALOR) {
+        const uint32_t i = MO_SUB + tid;
+        S.yw[pad_idx(i)] = (i < nw) ? rw[2 * i] : 0.0;
+      }
     }
     __syncthreads();
-    const uint32_t i0 = tid * CHUNK;
-    if (i0 < len) lag_chunk(ya, yw, 0, i0, min((uint32_t)CHUNK, len - i0), acc);
+    if (tid == 0 && sub + MO_SUB < b) stage(sub + MO_SUB);
+    const uint32_t i0 = ct * CHUNK;
+    if (i0 < len) {
+      const uint32_t nvalid = min((uint32_t)CHUNK, len - i0);
+      double va[CHUNK], w[2 * CHUNK];
+      load16(&S.ya[ct * (CHUNK + 2)], va);
+      load16(&S.yw[(ct + hb) * (CHUNK + 2)], w);
+      load16(&S.yw[(ct + hb + 1) * (CHUNK + 2)], w + CHUNK);
+#pragma unroll
+      for (int s = 0; s < CHUNK; ++s) {
+        const double v = ((uint32_t)s < nvalid) ? va[s] : 0.0;
+#pragma unroll
+        for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + l], acc[l]);
+      }
+    }
+    __syncthreads();
   }
   const double tot = warp_reduce_16(*reinterpret_cast<double (*)[16]>(acc));
+  if (lane < LAGB) S.red[hb][wp][lane] = tot;
   __syncthreads();
-  if (lane < LAGB) red[wp][lane] = tot;
-  __syncthreads();
-  if (tid < LAGB) {
-    double v = red[0][tid];
+  if (ct < LAGB) {
+    double v = S.red[hb][0][ct];
 #pragma unroll
-    for (int k = 1; k < MO_NT / 32; ++k) v += red[k][tid];
-    partr[(((size_t)blockIdx.y * g.C + c) * g.nunits + u) * LAGB + tid] = v;
+    for (int k = 1; k < MO_NT / 32; ++k) v += S.red[hb][k][ct];
+    partr[(((size_t)blockIdx.y * g.C + c) * g.nunits + u) * LAGR + hb * LAGB + ct] = v;
   }
 }
 
-// block-wide sums of n values (n <= 18) over DEC_NT = 64 threads, fixed order; result in out[] (shared)
-__device__ __forceinline__ void dec_reduce(double* vals, int n, double (*red)[20], double* out) {
+constexpr int DEC_RED = LAGR + 2;
+// block-wide sums of n values (n <= DEC_RED) over DEC_NT = 64 threads, fixed order; result in out[] (shared)
+__device__ __forceinline__ void dec_reduce(double* vals, int n, double (*red)[DEC_RED], double* out) {
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   for (int k = 0; k < n; ++k) {
     double v = vals[k];
@@ -226,11 +360,11 @@ __device__ __forceinline__ void dec_reduce(double* vals, int n, double (*red)[20
   __syncthreads();
 }
 
-// rho_t for the 16 lags of this round; returns true when the walk is finished.
-__device__ __forceinline__ bool rho_walk(const double* lagsum, uint32_t t0, uint32_t N, uint32_t C, double varhat,
+// rho_t for the nl lags of this round; returns true when the walk is finished.
+__device__ __forceinline__ bool rho_walk(const double* lagsum, int nl, uint32_t t0, uint32_t N, uint32_t C, double varhat,
                                          double& rho_sum, long long& lag_out) {
   const double mv = (double)C * varhat;
-  for (int l = 0; l < LAGB; ++l) {
+  for (int l = 0; l < nl; ++l) {
     const uint32_t t = t0 + l;
     if (t >= N) return true;
     const double rho = (lagsum[l] / (double)(N - t)) / mv;
@@ -246,8 +380,8 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
   extern __shared__ double dsm[];
   double* cm = dsm;          // [C] unsplit means
   double* hm = dsm + g.C;    // [2C] split means
-  __shared__ double red[DEC_NT / 32][20];
-  __shared__ double tot[20];
+  __shared__ double red[DEC_NT / 32][DEC_RED];
+  __shared__ double tot[DEC_RED];
   const int item = blockIdx.x, p = item >> 1, kind = item & 1;
   const uint32_t C = g.C, N = g.N, half = g.half;
   const double dn = (double)N, dh = (double)half;
@@ -258,28 +392,40 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
   for (uint32_t c = threadIdx.x; c < C; c += DEC_NT) {
     const double* pc = st.part + (((size_t)p * C + c) * g.nunits * 2 + kind) * MO_VALS;
     const double* y = reinterpret_cast<const double*>(zz + ((size_t)p * C + c) * N) + kind;
-    double s1 = 0, q1 = 0, mn1 = inf, mx1 = -inf, s2 = 0, q2 = 0, mn2 = inf, mx2 = -inf;
+    double s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+    // a half (or the whole chain) is constant iff no unit saw a draw different from its first
+    // one and all those first draws agree: its variance is then exactly 0 (diagnostics.py:196-201)
+    bool k1 = true, k2 = true, seen1 = false, seen2 = false;
+    double r1 = 0.0, r2 = 0.0;
     double R[LAGB];
     for (int l = 0; l < LAGB; ++l) R[l] = 0.0;
     for (uint32_t u = 0; u < g.nunits; ++u) {
       const double* pu = pc + (size_t)u * 2 * MO_VALS;
       for (int l = 0; l < LAGB; ++l) R[l] += pu[l];
       const double* sv = pu + LAGB;
-      if (u < g.nseg) { s1 += sv[0]; q1 += sv[1]; mn1 = fmin(mn1, sv[2]); mx1 = fmax(mx1, sv[3]); }
-      else            { s2 += sv[0]; q2 += sv[1]; mn2 = fmin(mn2, sv[2]); mx2 = fmax(mx2, sv[3]); }
+      if (sv[4] != 0.0) {
+        if (!seen1) { r1 = sv[2]; seen1 = true; }
+        s1 += sv[0]; q1 += sv[1]; k1 = k1 && (sv[3] == 0.0) && (sv[2] == r1);
+      }
+      if (sv[9] != 0.0) {
+        if (!seen2) { r2 = sv[7]; seen2 = true; }
+        s2 += sv[5]; q2 += sv[6]; k2 = k2 && (sv[8] == 0.0) && (sv[7] == r2);
+      }
     }
-    double sum = s1 + s2, sq = q1 + q2, mn = fmin(mn1, mn2), mx = fmax(mx1, mx2);
+    double sum = s1 + s2, sq = q1 + q2;
+    bool kf = k1 && k2 && (r1 == r2);
     if (N & 1u) {  // the draw dropped by the split
       const double yl = y[2 * (size_t)(N - 1)];
-      sum += yl; sq = fma(yl, yl, sq); mn = fmin(mn, yl); mx = fmax(mx, yl);
+      sum += yl; sq = fma(yl, yl, sq);
+      kf = kf && (half == 0 || yl == r1);
     }
     const double m1 = s1 / dh, m2 = s2 / dh, mf = sum / dn;
     double v1 = 0.0, v2 = 0.0, vf = 0.0;
     if (half >= 2) {
-      if (mn1 != mx1) v1 = fmax(0.0, (q1 - s1 * m1) / (dh - 1.0));
-      if (mn2 != mx2) v2 = fmax(0.0, (q2 - s2 * m2) / (dh - 1.0));
+      if (!k1) v1 = fmax(0.0, (q1 - s1 * m1) / (dh - 1.0));
+      if (!k2) v2 = fmax(0.0, (q2 - s2 * m2) / (dh - 1.0));
     }
-    if (N >= 2 && mn != mx) vf = fmax(0.0, (sq - sum * mf) / (dn - 1.0));
+    if (N >= 2 && !kf) vf = fmax(0.0, (sq - sum * mf) / (dn - 1.0));
     cm[c] = mf; hm[2 * c] = m1; hm[2 * c + 1] = m2;
     vals[0] += v1 + v2;
     vals[1] += vf;
@@ -336,7 +482,7 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
       } else {
         double rho_sum = 0.0;
         long long lag = (long long)N;
-        if (rho_walk(tot + 2, 1, N, C, var_hat, rho_sum, lag)) {
+        if (rho_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, lag)) {
           st.ess[o] = (double)C * dn / (1.0 + 2.0 * rho_sum);
           st.lag[o] = lag;
         } else {
@@ -349,25 +495,25 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
   }
 }
 
-// ---------------------------------------------------------------- later rounds: lags t0 .. t0+15 of the listed items
+// ---------------------------------------------------------------- later rounds: lags t0 .. t0+31 of the listed items
 __global__ void __launch_bounds__(DEC_NT) k_decide_r(const double2* __restrict__ zz, ChainGeom g, int PB, uint32_t t0,
                                                      int cur, ChainState st) {
-  __shared__ double red[DEC_NT / 32][20];
-  __shared__ double tot[20];
+  __shared__ double red[DEC_NT / 32][DEC_RED];
+  __shared__ double tot[DEC_RED];
   const int item = st.wl[cur][blockIdx.x], p = item >> 1, kind = item & 1;
   const uint32_t C = g.C, N = g.N;
-  double vals[LAGB];
-  for (int k = 0; k < LAGB; ++k) vals[k] = 0.0;
+  double vals[LAGR];
+  for (int k = 0; k < LAGR; ++k) vals[k] = 0.0;
   for (uint32_t c = threadIdx.x; c < C; c += DEC_NT) {
-    const double* pc = st.partr + ((size_t)blockIdx.x * C + c) * g.nunits * LAGB;
+    const double* pc = st.partr + ((size_t)blockIdx.x * C + c) * g.nunits * LAGR;
     const double* y = reinterpret_cast<const double*>(zz + ((size_t)p * C + c) * N) + kind;
-    double R[LAGB];
-    for (int l = 0; l < LAGB; ++l) R[l] = 0.0;
+    double R[LAGR];
+    for (int l = 0; l < LAGR; ++l) R[l] = 0.0;
     for (uint32_t u = 0; u < g.nunits; ++u)
-      for (int l = 0; l < LAGB; ++l) R[l] += pc[(size_t)u * LAGB + l];
+      for (int l = 0; l < LAGR; ++l) R[l] += pc[(size_t)u * LAGR + l];
     const double mf = st.cmean[(size_t)item * C + c], sum = st.csum[(size_t)item * C + c];
     double hs = st.head[(size_t)item * C + c], ts = st.tail[(size_t)item * C + c];
-    for (int l = 0; l < LAGB; ++l) {
+    for (int l = 0; l < LAGR; ++l) {
       const uint32_t t = t0 + l;
       if (t < N) {
         hs += y[2 * (size_t)(t - 1)];
@@ -378,12 +524,12 @@ __global__ void __launch_bounds__(DEC_NT) k_decide_r(const double2* __restrict__
     st.head[(size_t)item * C + c] = hs;
     st.tail[(size_t)item * C + c] = ts;
   }
-  dec_reduce(vals, LAGB, red, tot);
+  dec_reduce(vals, LAGR, red, tot);
   if (threadIdx.x == 0) {
     const size_t o = (size_t)kind * PB + p;
     double rho_sum = st.rhosum[item];
     long long lag = (long long)N;
-    if (rho_walk(tot, t0, N, C, st.varhat[item], rho_sum, lag)) {
+    if (rho_walk(tot, LAGR, t0, N, C, st.varhat[item], rho_sum, lag)) {
       st.ess[o] = (double)C * (double)N / (1.0 + 2.0 * rho_sum);
       st.lag[o] = lag;
     } else {

@@ -21,7 +21,7 @@
 
 namespace b200ref {
 
-constexpr int RANK_NT = 256;
+constexpr int RANK_NT = 128;
 constexpr int RANK_IPT = 8;
 constexpr int RANK_TILE = RANK_NT * RANK_IPT;
 
@@ -235,10 +235,17 @@ struct FoldOut {
   double* rankf;
 };
 
-__global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
-  __shared__ uint64_t sd[RANK_TILE];      // left window then right window (folded bits)
-  __shared__ uint32_t st[RANK_TILE];      // their positions in the sorted sequence
-  __shared__ uint64_t sv[RANK_SV];        // merged (padded index)
+// One CTA = RANK_TILE consecutive outputs of the folded (merged) order.
+//  phase 1  every global read of the tile is issued up front and coalesced: the left / right
+//           windows of the sorted sequence (keys -> folded bits, original positions, bulk tie codes);
+//  phase 2  per-thread merge path + serial merge in shared memory, tie detection (rare path: tie codes);
+//  phase 3  striped over the outputs: two table lookups and ONE 16-byte scatter per draw.
+__global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
+  __shared__ uint64_t sd[RANK_TILE];      // left window then right window (folded bits); later: tie codes
+  __shared__ uint32_t sp[RANK_TILE];      // original positions of the window elements
+  __shared__ uint32_t sc[RANK_TILE];      // bulk tie codes k = i + j of the window elements
+  __shared__ uint16_t ssrc[RANK_TILE];    // merged output -> window slot
+  __shared__ uint64_t sv[RANK_SV];        // merged folded bits (padded index)
   __shared__ uint32_t ext[2];
   __shared__ uint32_t scan_sm[RANK_NT / 32];
   const int p = blockIdx.y;
@@ -255,10 +262,15 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
   const uint32_t nl = a1 - a0, nr = c1 - c0;
   const bool has_prev = gbase > 0, has_next = gbase + n < M;
 
-  for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) {
-    const uint32_t t = (e < nl) ? (f.m0 - 1 - (a0 + e)) : (f.m0 + c0 + (e - nl));
-    sd[e] = f.fbits(t);
-    st[e] = t;
+#pragma unroll
+  for (int it = 0; it < RANK_IPT; ++it) {
+    const uint32_t e = it * RANK_NT + threadIdx.x;
+    if (e < n) {
+      const uint32_t t = (e < nl) ? (f.m0 - 1 - (a0 + e)) : (f.m0 + c0 + (e - nl));
+      sd[e] = f.fbits(t);
+      sp[e] = idx[t];
+      sc[e] = kc[t];
+    }
   }
   if (threadIdx.x == 0) {
     // merged element just before the tile: the larger of the two preceding heads
@@ -276,7 +288,6 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
   __syncthreads();
 
   // per-thread merge path inside the tile
-  uint32_t mt[RANK_IPT];
   {
     const uint32_t od = min((uint32_t)threadIdx.x * RANK_IPT, n);
     uint32_t lo = (od > nr) ? od - nr : 0, hi = min(od, nl);
@@ -285,17 +296,16 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
       if (sd[mid] <= sd[nl + od - 1 - mid]) lo = mid + 1; else hi = mid;
     }
     uint32_t la = lo, lc = od - lo;
+    uint64_t vl = (la < nl) ? sd[la] : ~0ull, vr = (lc < nr) ? sd[nl + lc] : ~0ull;
 #pragma unroll
     for (int it = 0; it < RANK_IPT; ++it) {
       const uint32_t e = od + it;
-      mt[it] = 0;
       if (e < n) {
-        const bool takeL = (la < nl) && (lc >= nr || sd[la] <= sd[nl + lc]);
-        const uint32_t src = takeL ? la : nl + lc;
-        sv[pidx8(e + 1)] = sd[src];
-        mt[it] = st[src];
-        la += takeL ? 1u : 0u;
-        lc += takeL ? 0u : 1u;
+        const bool takeL = (la < nl) && (lc >= nr || vl <= vr);
+        sv[pidx8(e + 1)] = takeL ? vl : vr;
+        ssrc[e] = (uint16_t)(takeL ? la : nl + lc);
+        if (takeL) { ++la; vl = (la < nl) ? sd[la] : ~0ull; }
+        else       { ++lc; vr = (lc < nr) ? sd[nl + lc] : ~0ull; }
       }
     }
   }
@@ -323,34 +333,20 @@ __global__ void __launch_bounds__(RANK_NT) k_fold(RankBufs b, uint32_t M, uint32
       const uint32_t e = threadIdx.x * RANK_IPT + it;
       if (e < n) sk[e] = k[it];
     }
+    __syncthreads();
   }
-  // st is dead too: it now holds, per merged position, the source position in the sorted sequence
-#pragma unroll
-  for (int it = 0; it < RANK_IPT; ++it) {
-    const uint32_t e = threadIdx.x * RANK_IPT + it;
-    if (e < n) st[e] = mt[it];
-  }
-  __syncthreads();
-  // striped output: consecutive lanes -> consecutive merged positions, so the table and
-  // (idx, kcode) reads are near-coalesced; only the final 16-byte scatter is random.
+  // striped output: consecutive lanes -> consecutive merged positions; both table lookups of the
+  // thread's outputs are issued before any is used, then only the 16-byte scatter is random.
   const size_t pbase = (size_t)p * M;
-  // all gathers of the thread's 8 outputs are issued before any is used (memory-level parallelism)
-  uint32_t tt[RANK_IPT], kk[RANK_IPT], pos[RANK_IPT], kcv[RANK_IPT];
-#pragma unroll
-  for (int it = 0; it < RANK_IPT; ++it) {
-    const uint32_t e = it * RANK_NT + threadIdx.x;
-    tt[it] = (e < n) ? st[e] : 0;
-    kk[it] = any_tie ? ((e < n) ? sk[e] : 1u) : 2u * (gbase + min(e, n - 1)) + 1u;
-  }
-#pragma unroll
-  for (int it = 0; it < RANK_IPT; ++it) {
-    pos[it] = idx[tt[it]];
-    kcv[it] = kc[tt[it]];
-  }
+  uint32_t pos[RANK_IPT], kk[RANK_IPT];
   double zb[RANK_IPT], zf[RANK_IPT];
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
-    zb[it] = b.ztab[kcv[it]];
+    const uint32_t e = it * RANK_NT + threadIdx.x;
+    const uint32_t src = (e < n) ? ssrc[e] : 0;
+    pos[it] = sp[src];
+    kk[it] = any_tie ? ((e < n) ? sk[e] : 1u) : 2u * (gbase + min(e, n - 1)) + 1u;
+    zb[it] = b.ztab[(e < n) ? sc[src] : 1u];
     zf[it] = b.ztab[kk[it]];
   }
 #pragma unroll

@@ -7,7 +7,7 @@
 A step = one full pass over the workload's parameter shard: sort -> tie ranks -> normal
 scores (raw + folded) -> split R-hat, bulk/tail ESS, mean/std/quantiles of the candidate
 draws; mean/std/quantiles of the reference draws; compare verdicts (tol 0.15); for N > 1
-the NCCL gather of the [P, 16] summaries and the AND of the verdicts.
+the NCCL gather of the [P, 20] summaries and the AND of the verdicts.
 
 Workloads (per GPU, weak scaling: parameters are sharded by column):
   c2      1000 params x 16 chains x 10000 draws + 10x1000 reference draws  (BASELINE configs[1])
@@ -90,8 +90,8 @@ class ClockSampler:
 
 
 def algorithmic_bytes(w: dict) -> int:
-    """every fp64 draw read once + 16 output doubles per parameter."""
-    return 8 * w["P"] * (w["C"] * w["N"] + w["RC"] * w["RN"]) + 8 * 16 * w["P"]
+    """every fp64 draw read once + the summary row (20 doubles) per parameter."""
+    return 8 * w["P"] * (w["C"] * w["N"] + w["RC"] * w["RN"]) + 8 * 20 * w["P"]
 
 
 def gpu_arm(args) -> None:
@@ -115,7 +115,7 @@ def gpu_arm(args) -> None:
     ws_cap = int(args.ws_gb * 2**30)
 
     def step():
-        # this rank's parameter block, then the [P/G, 16] summary gather + verdict AND (NCCL)
+        # this rank's parameter block, then the [P/G, 20] summary gather + verdict AND (NCCL)
         summary, passed = batch.full_pass(cand, ref, tolerance=TOL, workspace=ws, ws_cap_bytes=ws_cap)
         if world > 1:
             sharding.gather_summaries(summary, world * P)
@@ -196,7 +196,7 @@ def gpu_arm(args) -> None:
     # ---- end to end from HOST buffers through the public call (H2D + D2H inside the timed region) ----
     cand_h = cand.cpu().pin_memory()
     ref_h = ref.cpu().pin_memory()
-    sum_h = torch.empty((P, 16), dtype=torch.float64).pin_memory()
+    sum_h = torch.empty((P, len(batch.SUMMARY_COLUMNS)), dtype=torch.float64).pin_memory()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
 
     def e2e_step():
@@ -216,7 +216,7 @@ def gpu_arm(args) -> None:
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e = {"value": dp_per_step * e2e_steps / float(e2e_s.item()), "unit": UNIT,
-           "h2d_bytes_per_step": 8 * P * (C * N + MREF) * world, "d2h_bytes_per_step": 8 * 16 * P * world,
+           "h2d_bytes_per_step": 8 * P * (C * N + MREF) * world, "d2h_bytes_per_step": 8 * len(batch.SUMMARY_COLUMNS) * P * world,
            "steps": e2e_steps, "call": "mcmc_ref_b200.batch.full_pass_host -> b200ref_full_pass_host_f64 (pinned host buffers)"}
     same_bits = bool(np.array_equal(s_host.numpy(), summary.cpu().numpy(), equal_nan=True))
 

@@ -130,7 +130,7 @@ int b200ref_checks_f64(const double* rhat_dev, const double* ess_bulk_dev, int64
  *   out_host   [P][B200REF_SUMMARY_K] doubles, see B200REF_S_* below
  * Replaces reference.compare + diagnostics_for_model's per-parameter loop
  * (reference.py:76-122).  Returns the overall compare verdict in *passed_host. */
-#define B200REF_SUMMARY_K 16
+#define B200REF_SUMMARY_K 20
 #define B200REF_S_RHAT 0
 #define B200REF_S_ESS_BULK 1
 #define B200REF_S_ESS_TAIL 2
@@ -147,16 +147,27 @@ int b200ref_checks_f64(const double* rhat_dev, const double* ess_bulk_dev, int64
 #define B200REF_S_REL_MEAN 13
 #define B200REF_S_REL_STD 14
 #define B200REF_S_FLAGS 15 /* bit0 mean passed, bit1 std passed (stored as double) */
+/* EXTENSION columns (north-star MCSE / z-score check; the reference has neither -- compare.py is
+ * relative-error only -- so parity is pinned against the oracle's definition, and these never
+ * change the compare verdict):
+ *   mcse_mean   = std / sqrt(ess_bulk)                       (candidate)
+ *   ref_se_mean = ref_std / sqrt(Mref)                       (reference draws are thinned: taken as independent)
+ *   z_mean      = (mean - ref_mean) / sqrt(mcse_mean^2 + ref_se_mean^2)
+ *   z_pass      = 1.0 if |z_mean| <= z_crit else 0.0        (NaN fails) */
+#define B200REF_S_MCSE_MEAN 16
+#define B200REF_S_REF_SE_MEAN 17
+#define B200REF_S_Z_MEAN 18
+#define B200REF_S_Z_PASS 19
 
 /* Device-resident form: inputs already in HBM, summary written to device. */
 int b200ref_full_pass_f64(const double* cand_dev, int64_t P, int64_t C, int64_t N,
-                          const double* ref_dev, int64_t Mref, double tol,
-                          double* summary_dev /* [P][16] */, uint8_t* passed_host,
+                          const double* ref_dev, int64_t Mref, double tol, double z_crit,
+                          double* summary_dev /* [P][B200REF_SUMMARY_K] */, uint8_t* passed_host,
                           void* ws_dev, size_t ws_bytes, void* stream);
 
 int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, int64_t N,
-                               const double* ref_host, int64_t Mref, double tol,
-                               double* summary_host /* [P][16] */, uint8_t* passed_host,
+                               const double* ref_host, int64_t Mref, double tol, double z_crit,
+                               double* summary_host /* [P][B200REF_SUMMARY_K] */, uint8_t* passed_host,
                                void* ws_dev, size_t ws_bytes);
 
 /* Batched log-density of the logistic-regression GLM (Stan: y ~ bernoulli_logit(X * beta)):

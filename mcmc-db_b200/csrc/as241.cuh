@@ -64,13 +64,16 @@ __device__ __forceinline__ double as241_inv_cdf(double p) {
 // avg_rank = (i + 1 + j) / 2.0 (diagnostics.py:118) and p = (avg_rank - 0.5) / n
 // (:130) give p = ((i + j) / 2) / n with a single rounding (the divide), so
 // k = i + j indexes every value z can take.  2M entries, L2-resident.
-__global__ void k_ztable(double* __restrict__ tab, uint32_t m) {
+// odd[t] = T[2t + 1] is the score of an untied draw at sorted position t: a dense copy that the
+// fold kernel reads coalesced (ties, the rare case, go to T itself).
+__global__ void k_ztable(double* __restrict__ tab, double* __restrict__ odd, uint32_t m) {
   const uint32_t n = 2u * m;
   const double dm = (double)m;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     double z = 0.0;
     if (k > 0) z = as241_inv_cdf(__ddiv_rn(rmul((double)k, 0.5), dm));
     tab[k] = z;
+    if (k & 1u) odd[k >> 1] = z;
   }
 }
 

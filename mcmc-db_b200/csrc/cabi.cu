@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -103,7 +104,7 @@ inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 
 // Workspace carve-up for one batch of PB parameters with M pooled draws each.
 struct Layout {
-  size_t ztab, flag, header;  // shared part
+  size_t ztab, zodd, flag, header;  // shared part
   size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
       crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cwl0, cwl1, cnwl, per_batch;
   uint32_t ntiles, nchunks;
@@ -112,6 +113,7 @@ struct Layout {
     nchunks = (uint32_t)((M + CHUNK_P - 1) / CHUNK_P);
     size_t o = 0;
     ztab = o; o += up(2 * (size_t)M * sizeof(double));
+    zodd = o; o += up((size_t)M * sizeof(double));
     flag = o; o += up(sizeof(int));
     header = o;
     size_t b = 0;
@@ -240,7 +242,8 @@ __global__ void k_checks(const double* __restrict__ rhat, const double* __restri
 // Summary rows [P][16] of the fused pass (include/b200ref.h B200REF_S_*).
 __global__ void k_summary(const double* rhat, const double* essb, const double* esst, const double* mean,
                           const double* sd, const double* q, const double* rmean, const double* rsd,
-                          const double* rq, double tol, int64_t P, double* out, int* nfail) {
+                          const double* rq, double tol, double z_crit, int64_t Mref, int64_t P, double* out,
+                          int* nfail) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   double* o = out + p * B200REF_SUMMARY_K;
@@ -272,6 +275,16 @@ __global__ void k_summary(const double* rhat, const double* essb, const double* 
   }
   o[B200REF_S_FLAGS] = (double)flags;
   if (flags != 3) atomicAdd(nfail, 1);
+  {  // extension: Monte-Carlo standard errors and the z-score of the mean difference
+    const double se_c = __ddiv_rn(sd[p], __dsqrt_rn(essb[p]));
+    const double se_r = __ddiv_rn(rsd[p], __dsqrt_rn((double)Mref));
+    const double z = __ddiv_rn(__dsub_rn(mean[p], rmean[p]),
+                               __dsqrt_rn(__dadd_rn(__dmul_rn(se_c, se_c), __dmul_rn(se_r, se_r))));
+    o[B200REF_S_MCSE_MEAN] = se_c;
+    o[B200REF_S_REF_SE_MEAN] = se_r;
+    o[B200REF_S_Z_MEAN] = z;
+    o[B200REF_S_Z_PASS] = (fabs(z) <= z_crit) ? 1.0 : 0.0;
+  }
 }
 
 struct Mode {
@@ -299,6 +312,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   L.compute(PBmax, M, ws_zz, C, N);
   char* w = (char*)ws;
   double* ztab = (double*)(w + L.ztab);
+  double* zodd = (double*)(w + L.zodd);
   int* flag = (int*)(w + L.flag);
   char* wb = w + L.header;
   static bool part_attr = false;
@@ -313,7 +327,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
 
   CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
   const bool want_scores = need_z || z_b || z_f || rank_f;
-  if (want_scores) LAUNCH(K_ZTABLE, st, k_ztable<<<296, 256, 0, st>>>(ztab, (uint32_t)M));
+  if (want_scores) LAUNCH(K_ZTABLE, st, k_ztable<<<296, 256, 0, st>>>(ztab, zodd, (uint32_t)M));
   QuantArgs qa;
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q_host[i];
@@ -375,6 +389,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     rb.m0 = (uint32_t*)(wb + L.m0);
     rb.apos = (uint32_t*)(wb + L.apos);
     rb.ztab = ztab;
+    rb.zodd = zodd;
+    rb.flag = flag;
     const dim3 gt(L.ntiles, PB);
     {
       // while per-kernel timing is on, the fallback runs on the main stream so that every
@@ -604,8 +620,8 @@ int b200ref_checks_f64(const double* rhat, const double* essb, int64_t P, uint8_
 static size_t fused_tail_bytes(int64_t P) { return up((size_t)P * 13 * 8) + up(16); }
 
 int b200ref_full_pass_f64(const double* cand, int64_t P, int64_t C, int64_t N, const double* ref, int64_t Mref,
-                          double tol, double* summary, uint8_t* passed_host, void* ws, size_t ws_bytes,
-                          void* stream) {
+                          double tol, double z_crit, double* summary, uint8_t* passed_host, void* ws,
+                          size_t ws_bytes, void* stream) {
   g_err[0] = 0;
   if (!cand || !ref || !summary || P < 1 || Mref < 1) return fail(B200REF_ERR_ARG, "bad full_pass arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -628,8 +644,8 @@ int b200ref_full_pass_f64(const double* cand, int64_t P, int64_t C, int64_t N, c
   rc = run(ref, P, 1, Mref, qs, 3, &orf, nullptr, nullptr, nullptr, nullptr, Mode{false, false}, ws, body, st);
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(nfail, 0, sizeof(int), st));
-  LAUNCH(K_SUMMARY, st, k_summary<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(rhat, essb, esst, mean, sd, q, rmean, rsd, rq, tol, P,
-                                                         summary, nfail));
+  LAUNCH(K_SUMMARY, st, k_summary<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(rhat, essb, esst, mean, sd, q, rmean, rsd, rq, tol, z_crit,
+                                                         Mref, P, summary, nfail));
   int h = 0;
   CUDA_TRY(cudaMemcpyAsync(&h, nfail, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -639,8 +655,8 @@ int b200ref_full_pass_f64(const double* cand, int64_t P, int64_t C, int64_t N, c
 }
 
 int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, int64_t N, const double* ref_host,
-                               int64_t Mref, double tol, double* summary_host, uint8_t* passed_host, void* ws,
-                               size_t ws_bytes) {
+                               int64_t Mref, double tol, double z_crit, double* summary_host, uint8_t* passed_host,
+                               void* ws, size_t ws_bytes) {
   g_err[0] = 0;
   if (!cand_host || !ref_host || !summary_host || P < 1) return fail(B200REF_ERR_ARG, "bad full_pass_host arguments");
   // Stage inputs in parameter slabs: two slabs in flight, H2D of slab k+1 on the copy
@@ -696,7 +712,7 @@ int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, in
       double* dsum = dr + (size_t)slab * Mref;
       cudaStreamWaitEvent(s_comp, copied[b], 0);
       uint8_t ok = 0;
-      rc = b200ref_full_pass_f64(dc, pb, C, N, dr, Mref, tol, dsum, &ok, cws, cws_bytes, s_comp);
+      rc = b200ref_full_pass_f64(dc, pb, C, N, dr, Mref, tol, z_crit, dsum, &ok, cws, cws_bytes, s_comp);
       if (rc) break;
       all_ok &= ok;
       cudaMemcpyAsync(summary_host + (size_t)p0 * B200REF_SUMMARY_K, dsum, (size_t)pb * B200REF_SUMMARY_K * 8,

@@ -37,6 +37,8 @@ struct RankBufs {
   uint32_t* m0;        // [PB] number of draws strictly below the median
   uint32_t* apos;      // [PB][ntiles+1] merge-path split (count taken from the left part)
   const double* ztab;  // [2M]
+  const double* zodd;  // [M]  zodd[t] = ztab[2t + 1]
+  const int* flag;     // bit0: non-finite input seen -> the ordering is meaningless, kernels return
 };
 
 __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t lo, uint32_t hi, uint64_t v) {
@@ -83,7 +85,7 @@ struct QuantArgs {
 
 __global__ void k_param_prep(RankBufs b, uint32_t M, int PB, QuantArgs qa, PrepOut o) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= PB) return;
+  if (p >= PB || (*b.flag & 1)) return;
   const uint64_t* keys = b.key[b.sel[p]] + (size_t)p * M;
   double med;
   if (M & 1u) med = key2dbl(keys[M / 2]);
@@ -222,7 +224,7 @@ struct FoldView {
 __global__ void k_merge_partition(RankBufs b, uint32_t M, uint32_t ntiles, int PB) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   const int p = blockIdx.y;
-  if (q > ntiles || p >= PB) return;
+  if (q > ntiles || p >= PB || (*b.flag & 1)) return;
   FoldView f{b.key[b.sel[p]] + (size_t)p * M, b.m0[p], M, b.med[p]};
   const uint32_t o = min(q * (uint32_t)RANK_TILE, M);
   b.apos[(size_t)p * (ntiles + 1) + q] = f.split(o);
@@ -243,13 +245,14 @@ struct FoldOut {
 __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
   __shared__ uint64_t sd[RANK_TILE];      // left window then right window (folded bits); later: tie codes
   __shared__ uint32_t sp[RANK_TILE];      // original positions of the window elements
-  __shared__ uint32_t sc[RANK_TILE];      // bulk tie codes k = i + j of the window elements
+  __shared__ double szb[RANK_TILE];       // bulk scores of the window elements
   __shared__ uint16_t ssrc[RANK_TILE];    // merged output -> window slot
   __shared__ uint64_t sv[RANK_SV];        // merged folded bits (padded index)
   __shared__ uint32_t ext[2];
   __shared__ uint32_t scan_sm[RANK_NT / 32];
   const int p = blockIdx.y;
   const uint32_t tile = blockIdx.x;
+  if (*b.flag & 1) return;
   const int s = b.sel[p];
   const uint32_t* idx = b.idx[s] + (size_t)p * M;
   const uint32_t* kc = b.kcode + (size_t)p * M;
@@ -262,15 +265,43 @@ __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, ui
   const uint32_t nl = a1 - a0, nr = c1 - c0;
   const bool has_prev = gbase > 0, has_next = gbase + n < M;
 
+  // loads are issued in two batches of RANK_IPT / 2 (clamped indices, no branches) so that every
+  // warp has 16 independent requests in flight instead of one dependent chain per element
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    constexpr int HB = RANK_IPT / 2;
+    uint32_t tt[HB], pi[HB], kcv[HB];
+    uint64_t kv[HB];
+    double zo[HB];
+#pragma unroll
+    for (int j = 0; j < HB; ++j) {
+      const uint32_t e = min((h * HB + j) * RANK_NT + threadIdx.x, n - 1);
+      tt[j] = (e < nl) ? (f.m0 - 1 - (a0 + e)) : (f.m0 + c0 + (e - nl));
+    }
+#pragma unroll
+    for (int j = 0; j < HB; ++j) {
+      kv[j] = f.keys[tt[j]];
+      pi[j] = idx[tt[j]];
+      kcv[j] = kc[tt[j]];
+    }
+    // bulk scores: T[k], k = 2t + 1 for an untied draw -> neighbouring table entries
+#pragma unroll
+    for (int j = 0; j < HB; ++j) zo[j] = b.ztab[min(kcv[j], 2u * M - 1u)];
+    // (slots past the end of a short last tile repeat element n - 1: identical values, same address)
+#pragma unroll
+    for (int j = 0; j < HB; ++j) {
+      const uint32_t e = min((h * HB + j) * RANK_NT + threadIdx.x, n - 1);
+      sd[e] = (uint64_t)__double_as_longlong(fabs(__dsub_rn(key2dbl(kv[j]), f.med)));
+      sp[e] = pi[j];
+      szb[e] = zo[j];
+    }
+  }
+  // scores of the tile's outputs if the folded order has no ties here (the usual case)
+  double zfn[RANK_IPT];
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
     const uint32_t e = it * RANK_NT + threadIdx.x;
-    if (e < n) {
-      const uint32_t t = (e < nl) ? (f.m0 - 1 - (a0 + e)) : (f.m0 + c0 + (e - nl));
-      sd[e] = f.fbits(t);
-      sp[e] = idx[t];
-      sc[e] = kc[t];
-    }
+    zfn[it] = (e < n) ? b.zodd[gbase + e] : 0.0;
   }
   if (threadIdx.x == 0) {
     // merged element just before the tile: the larger of the two preceding heads
@@ -345,9 +376,9 @@ __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, ui
     const uint32_t e = it * RANK_NT + threadIdx.x;
     const uint32_t src = (e < n) ? ssrc[e] : 0;
     pos[it] = sp[src];
+    zb[it] = szb[src];
     kk[it] = any_tie ? ((e < n) ? sk[e] : 1u) : 2u * (gbase + min(e, n - 1)) + 1u;
-    zb[it] = b.ztab[(e < n) ? sc[src] : 1u];
-    zf[it] = b.ztab[kk[it]];
+    zf[it] = any_tie ? b.ztab[kk[it]] : zfn[it];
   }
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {

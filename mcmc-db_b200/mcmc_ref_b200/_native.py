@@ -13,7 +13,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libb200ref.so"
 
 ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_NONFINITE = -1, -2, -3, -4
-SUMMARY_K = 16
+SUMMARY_K = 20
 MAX_QUANTILES = 8
 
 EXPORTS = (
@@ -75,8 +75,8 @@ def load() -> C.CDLL:
     lib.b200ref_stats_f64.argtypes = [vp, i64, i64, C.POINTER(dbl), C.c_int, C.POINTER(Outputs), vp, sz, vp]
     lib.b200ref_compare_f64.argtypes = [vp, vp, i64, dbl, vp, vp, vp, vp]
     lib.b200ref_checks_f64.argtypes = [vp, vp, i64, C.POINTER(C.c_uint8), vp]
-    lib.b200ref_full_pass_f64.argtypes = [vp, i64, i64, i64, vp, i64, dbl, vp, C.POINTER(C.c_uint8), vp, sz, vp]
-    lib.b200ref_full_pass_host_f64.argtypes = [vp, i64, i64, i64, vp, i64, dbl, vp, C.POINTER(C.c_uint8), vp, sz]
+    lib.b200ref_full_pass_f64.argtypes = [vp, i64, i64, i64, vp, i64, dbl, dbl, vp, C.POINTER(C.c_uint8), vp, sz, vp]
+    lib.b200ref_full_pass_host_f64.argtypes = [vp, i64, i64, i64, vp, i64, dbl, dbl, vp, C.POINTER(C.c_uint8), vp, sz]
     lib.b200ref_synth_fill_f64.argtypes = [vp, i64, i64, i64, i64, u64, C.c_int, vp]
     lib.b200ref_glm_workspace_bytes.restype = sz
     lib.b200ref_glm_workspace_bytes.argtypes = [i64, i64, i64]

@@ -171,14 +171,19 @@ def checks_batch(rhat: torch.Tensor, ess_bulk: torch.Tensor) -> tuple[bool, bool
 
 
 SUMMARY_COLUMNS = ("rhat", "ess_bulk", "ess_tail", "mean", "std", "q5", "q50", "q95",
-                   "ref_mean", "ref_std", "ref_q5", "ref_q50", "ref_q95", "rel_mean", "rel_std", "flags")
+                   "ref_mean", "ref_std", "ref_q5", "ref_q50", "ref_q95", "rel_mean", "rel_std", "flags",
+                   # extension columns (no reference counterpart): MCSE of the mean, z-score check
+                   "mcse_mean", "ref_se_mean", "z_mean", "z_pass")
+Z_CRIT = 4.0  # default |z| bound of the (extension) z-score check
 
 
 def full_pass(cand, ref, tolerance: float = 0.15, workspace: Workspace | None = None,
-              ws_cap_bytes: int | None = None) -> tuple[torch.Tensor, bool]:
+              ws_cap_bytes: int | None = None, z_crit: float = Z_CRIT) -> tuple[torch.Tensor, bool]:
     """Device-resident fused pass: candidate [P, C, N] vs reference draws [P, Mref].
 
-    Returns (summary [P, 16] CUDA tensor, overall compare verdict on mean & std).
+    Returns (summary [P, len(SUMMARY_COLUMNS)] CUDA tensor, overall compare verdict on mean & std --
+    the reference's verdict, ``compare.py:38-51``; the z-score columns are an extension and never
+    enter it).
     """
     lib = _native.load()
     ct, rt = to_device(cand), to_device(ref)
@@ -188,14 +193,14 @@ def full_pass(cand, ref, tolerance: float = 0.15, workspace: Workspace | None = 
     ws = (workspace or _WS).for_shape(p, c, n, extra=p * 13 * 8 + 1024, cap_bytes=ws_cap_bytes)
     ok = C.c_uint8(0)
     _native.check(lib.b200ref_full_pass_f64(ct.data_ptr(), p, c, n, rt.data_ptr(), rt.shape[1], float(tolerance),
-                                            summary.data_ptr(), C.byref(ok), ws.data_ptr(), ws.numel(),
+                                            float(z_crit), summary.data_ptr(), C.byref(ok), ws.data_ptr(), ws.numel(),
                                             _stream_ptr()))
     return summary, bool(ok.value)
 
 
 def full_pass_host(cand_host: torch.Tensor, ref_host: torch.Tensor, tolerance: float = 0.15,
                    summary_host: torch.Tensor | None = None, workspace: Workspace | None = None,
-                   ws_bytes: int | None = None) -> tuple[torch.Tensor, bool]:
+                   ws_bytes: int | None = None, z_crit: float = Z_CRIT) -> tuple[torch.Tensor, bool]:
     """End-to-end pass from HOST buffers (pinned torch CPU tensors for full PCIe speed).
 
     The library stages parameter slabs through the workspace, overlapping H2D copies
@@ -213,12 +218,12 @@ def full_pass_host(cand_host: torch.Tensor, ref_host: torch.Tensor, tolerance: f
         summary_host = torch.empty((p, _native.SUMMARY_K), dtype=torch.float64, pin_memory=True)
     if ws_bytes is None:
         slab = min(p, 1024)
-        ws_bytes = (int(lib.b200ref_workspace_bytes(slab, c, n)) + 2 * slab * (c * n + mref + 16) * 8
+        ws_bytes = (int(lib.b200ref_workspace_bytes(slab, c, n)) + 2 * slab * (c * n + mref + _native.SUMMARY_K) * 8
                     + slab * 13 * 8 + 8192)
     ws = (workspace or _WS).ensure(ws_bytes)
     ok = C.c_uint8(0)
     _native.check(lib.b200ref_full_pass_host_f64(cand_host.data_ptr(), p, c, n, ref_host.data_ptr(), mref,
-                                                 float(tolerance), summary_host.data_ptr(), C.byref(ok),
+                                                 float(tolerance), float(z_crit), summary_host.data_ptr(), C.byref(ok),
                                                  ws.data_ptr(), ws.numel()))
     return summary_host, bool(ok.value)
 

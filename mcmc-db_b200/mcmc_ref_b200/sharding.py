@@ -2,7 +2,7 @@
 
 One process per GPU (torch.distributed; NCCL on GPUs, gloo in the CPU tests).  There is no
 data-path collective: each rank runs the full pass on its contiguous block of parameters;
-the only communication is one all_gather of the [P_local, 16] summary rows and one
+the only communication is one all_gather of the [P_local, 20] summary rows and one
 all_reduce(MIN) of the compare verdict.
 """
 

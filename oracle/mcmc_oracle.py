@@ -414,8 +414,23 @@ def checks(n_chains: int, n_draws: int, diag: dict) -> dict:
     }
 
 
+def zscore_extension(mean, std, ess_bulk, ref_mean, ref_std, mref: int, z_crit: float = 4.0) -> dict:
+    """EXTENSION (no reference code: ``compare.py`` is relative-error only; parity unpinned).
+
+    mcse_mean = std / sqrt(ess_bulk); ref_se_mean = ref_std / sqrt(Mref) (the packaged reference
+    draws are thinned, ``provenance.py:17-22``: taken as independent);
+    z_mean = (mean - ref_mean) / sqrt(mcse_mean**2 + ref_se_mean**2); z_pass = |z_mean| <= z_crit
+    (NaN fails).  Every operation is one IEEE rounding, in this order.
+    """
+    with np.errstate(all="ignore"):
+        se_c = np.asarray(std, dtype=np.float64) / np.sqrt(np.asarray(ess_bulk, dtype=np.float64))
+        se_r = np.asarray(ref_std, dtype=np.float64) / np.sqrt(np.float64(mref))
+        z = (np.asarray(mean, dtype=np.float64) - np.asarray(ref_mean, dtype=np.float64)) / np.sqrt(se_c * se_c + se_r * se_r)
+        return {"mcse_mean": se_c, "ref_se_mean": se_r, "z_mean": z, "z_pass": np.abs(z) <= z_crit}
+
+
 def full_pass(cand: np.ndarray, ref: np.ndarray, tolerance: float = 0.15,
-              quantiles=(0.05, 0.5, 0.95)) -> dict:
+              quantiles=(0.05, 0.5, 0.95), z_crit: float = 4.0) -> dict:
     """The benchmarked unit of work for P params:
 
     candidate [P, C, N]: mean/std (compare.py:58-64), quantiles + rhat/ess_bulk/ess_tail;
@@ -449,4 +464,6 @@ def full_pass(cand: np.ndarray, ref: np.ndarray, tolerance: float = 0.15,
     out["rel_mean"], out["pass_mean"] = compare_arrays(out["ref_mean"], out["mean"], tolerance)
     out["rel_std"], out["pass_std"] = compare_arrays(out["ref_std"], out["std"], tolerance)
     out["passed"] = bool(out["pass_mean"].all() and out["pass_std"].all())
+    out.update(zscore_extension(out["mean"], out["std"], out["ess_bulk"], out["ref_mean"], out["ref_std"],
+                                ref.shape[1], z_crit))
     return out

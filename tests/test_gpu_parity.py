@@ -341,6 +341,14 @@ def test_full_pass_device_and_host(B):
     assert np.array_equal((flags & 1) != 0, want["pass_mean"])
     assert np.array_equal((flags & 2) != 0, want["pass_std"])
     assert passed == want["passed"]
+    # extension columns (MCSE of the mean, z-score check): oracle-defined, tolerance-class
+    for name in ("mcse_mean", "ref_se_mean", "z_mean"):
+        assert_close_arr(got[:, cols.index(name)], want[name], TOL, name)
+    assert np.array_equal(got[:, cols.index("z_pass")] != 0, want["z_pass"])
+    s3, _ = B.full_pass(cand, ref, tolerance=0.15, z_crit=1.0)
+    want3 = O.full_pass(cand.cpu().numpy(), ref.cpu().numpy(), tolerance=0.15, z_crit=1.0)
+    assert np.array_equal(s3.cpu().numpy()[:, cols.index("z_pass")] != 0, want3["z_pass"])
+    assert want3["z_pass"].any() and not want3["z_pass"].all()  # both verdicts occur at |z| <= 1
     ch = cand.cpu().pin_memory()
     rh = ref.cpu().pin_memory()
     s_host, passed_h = B.full_pass_host(ch, rh, tolerance=0.15)
@@ -349,7 +357,7 @@ def test_full_pass_device_and_host(B):
     # slabs smaller than P: same bits
     lib = B._native.load()
     slab = 16
-    small_ws = int(lib.b200ref_workspace_bytes(slab, c, n)) + 2 * slab * (c * n + mref + 16) * 8 + slab * 13 * 8 + 8192
+    small_ws = int(lib.b200ref_workspace_bytes(slab, c, n)) + 2 * slab * (c * n + mref + len(cols)) * 8 + slab * 13 * 8 + 8192
     s_host2, _ = B.full_pass_host(ch, rh, tolerance=0.15, workspace=B.Workspace(), ws_bytes=small_ws)
     assert np.array_equal(s_host2.numpy(), got, equal_nan=True)
     torch.cuda.synchronize()

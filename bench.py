@@ -12,6 +12,7 @@ the NCCL gather of the [P, 20] summaries and the AND of the verdicts.
 Workloads (per GPU, weak scaling: parameters are sharded by column):
   c2      1000 params x 16 chains x 10000 draws + 10x1000 reference draws  (BASELINE configs[1])
   c5tile  12500 params x 64 chains x 4096 draws (1/8 of configs[4]; 8 GPUs = the full config)
+  c4      64 params x 8 chains x 1M draws (BASELINE configs[3], long-chain ESS stress)
   tiny    64 x 4 x 1000 (self-test)
 """
 
@@ -36,6 +37,8 @@ WORKLOADS = {
                name="c2: 1000 params x 16 chains x 10000 draws vs 10x1000 reference draws, per GPU"),
     "c5tile": dict(P=12500, C=64, N=4096, RC=10, RN=1000,
                    name="c5 shard: 12500 params x 64 chains x 4096 draws per GPU (8 GPUs = 100k params)"),
+    "c4": dict(P=64, C=8, N=1_000_000, RC=10, RN=1000,
+               name="c4: long-chain ESS stress, 64 params x 8 chains x 1M draws per GPU"),
     "tiny": dict(P=64, C=4, N=1000, RC=10, RN=100, name="tiny self-test 64 x 4 x 1000"),
 }
 METRIC = "diag+compare draw*params/s"

@@ -41,6 +41,8 @@ constexpr int PART_IPT = CHUNK_P / PART_NT;
 constexpr int FIN_NT = 256;
 constexpr int FIN_IPT = CAP1 / FIN_NT;
 constexpr int BIG_FINE = 32;      // fine buckets larger than this are handled warp-cooperatively
+constexpr int SUB_MAX = 32;       // equal-width sub-buckets per coarse bucket (long chains, M > ~330k)
+constexpr int NBW_MAX = NB1_MAX * SUB_MAX;  // buckets per parameter on the wide path
 
 // Per-parameter bucket function, written by k_sample.
 struct BucketFn {
@@ -50,13 +52,23 @@ struct BucketFn {
   double sp[NB1_MAX]; // sp[j], j = 0 .. nb1-2 : splitters (ascending); rest = +inf
   uint16_t lut[NCELL + 2];  // lut[c] = number of splitters whose cell is < c
   int nb1;
-  int pad;
+  int sub;            // sub-buckets per coarse bucket (1: the coarse buckets are the buckets)
+  double fsub[NB1_MAX];  // sub / (upper - lower) of coarse bucket c, 0 if degenerate
 };
 
 __host__ __device__ inline int choose_nb1(int64_t M) {
   int nb = 1;
   while (nb < NB1_MAX && M > (int64_t)nb * 768) nb <<= 1;
   return nb;
+}
+
+// sub-buckets per coarse bucket so that a bucket holds ~1000 draws (<= 1280 on average) up to
+// M = 10.5M pooled draws per parameter; beyond that buckets grow and the oversize paths take over.
+__host__ __device__ inline int choose_sub(int64_t M) {
+  const int nb1 = choose_nb1(M);
+  int sub = 1;
+  while (sub < SUB_MAX && M > (int64_t)nb1 * sub * 1280) sub <<= 1;
+  return sub;
 }
 
 __device__ __forceinline__ int cell_of(double x, double lo, double cs) {
@@ -75,6 +87,12 @@ __device__ __forceinline__ int coarse_of(double x, double lo, double cs, const d
   return a;
 }
 
+// sub-bucket of x inside coarse bucket c (lower bound lc, scale fsub = sub / width): monotone in x
+__device__ __forceinline__ int sub_of(double x, double lc, double fsub, int sub) {
+  const double t = (x - lc) * fsub;
+  return (t >= 0.0) ? ((t < (double)sub) ? (int)t : sub - 1) : 0;
+}
+
 // fine bucket inside a coarse bucket with bounds [L, U): floor((x - L) * fs), clamped
 __device__ __forceinline__ int fine_of(double x, double L, double fs) {
   const double t = (x - L) * fs;
@@ -84,7 +102,9 @@ __device__ __forceinline__ int fine_of(double x, double L, double fs) {
 struct BucketBufs {
   BucketFn* fn;        // [PB]
   uint32_t* cnt;       // [PB][nchunks][NB1_MAX]  per-chunk bucket counts -> exclusive offsets
-  uint32_t* boff;      // [PB][NB1_MAX + 1]       bucket start offsets in the sorted order
+  uint32_t* boff;      // [PB][bstride]           bucket start offsets in the sorted order (nbt + 1 used)
+  int bstride;         // NB1_MAX + 1 (narrow) or NBW_MAX + 1 (wide)
+  uint32_t* cur;       // [PB][NBW_MAX]           wide path: bucket totals, then write cursors
   double* spart;       // [PB][nchunks][2]        shifted power sums per chunk
   uint8_t* fallback;   // [PB] 1 = sort this parameter with the LSD path
   int* nbigb;          // number of oversize coarse buckets in this batch
@@ -141,6 +161,7 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     fn->lo = lo; fn->hi = hi; fn->cs = isfinite(cs) ? cs : 0.0;
     fn->c0 = key2dbl(s[S / 2]);
     fn->nb1 = nb1;
+    fn->sub = choose_sub(M);
     b.fallback[p] = 0;
     b.sel[p] = 1;
     if (p == 0) { *b.nfb = 0; *b.nbigb = 0; }
@@ -157,6 +178,17 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     scell[j] = c;
   }
   __syncthreads();
+  for (int j = threadIdx.x; j < NB1_MAX; j += 512) {
+    // scale of the sub-bucket / fine-bucket function of coarse bucket j
+    double fsv = 0.0;
+    if (j < nb1) {
+      const double L = (j == 0) ? lo : fn->sp[j - 1];
+      const double U = (j == nb1 - 1) ? hi : fn->sp[j];
+      if (U > L) fsv = (double)choose_sub(M) / (U - L);
+      if (!isfinite(fsv)) fsv = 0.0;
+    }
+    fn->fsub[j] = fsv;
+  }
   for (int c = threadIdx.x; c < NCELL + 2; c += 512) {
     // number of splitters with cell < c  (scell ascending over j < nb1-1, NCELL beyond)
     int a = 0, e = nb1 - 1;
@@ -249,8 +281,8 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
   uint32_t pre = 0;
   for (int k = 0; k < w; ++k) pre += wtot[k];
   const uint32_t excl = pre + incl - run;
-  b.boff[(size_t)p * (NB1_MAX + 1) + t] = excl;
-  if (t == NB1_MAX - 1) b.boff[(size_t)p * (NB1_MAX + 1) + NB1_MAX] = excl + run;
+  b.boff[(size_t)p * b.bstride + t] = excl;
+  if (t == NB1_MAX - 1) b.boff[(size_t)p * b.bstride + NB1_MAX] = excl + run;
   for (uint32_t c = 0; c < nchunks; ++c) cnt[(size_t)c * NB1_MAX + t] += excl;
   if (t == 0) {
     // mean = c0 + S1/M ; var = (S2 - S1^2/M)/M  (sums about the sample median: no cancellation)
@@ -285,7 +317,10 @@ struct PartSmem {
   uint8_t sbk[CHUNK_P];
 };
 
-__global__ void __launch_bounds__(PART_NT) k_partition(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
+#ifndef B200REF_PART_OCC
+#define B200REF_PART_OCC 3
+#endif
+__global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
                                                         BucketBufs b) {
   extern __shared__ __align__(16) unsigned char part_smem_raw[];
   PartSmem& sm = *reinterpret_cast<PartSmem*>(part_smem_raw);
@@ -416,6 +451,39 @@ __device__ __forceinline__ void fine_scan(FinSmem<CAP, NF>& sm) {
   if (tid == NT - 1) sm.foff[NF] = run;
 }
 
+// Warp-cooperative in-place ascending sort of n (value, position) pairs in shared memory: a bitonic
+// network whose compare-exchanges all point the same way, so a length that is not a power of two
+// just skips the pairs reaching past the end (the missing tail behaves as +inf).
+__device__ __forceinline__ void warp_sort_pairs(double* __restrict__ kd, uint32_t* __restrict__ iv, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t N = 2;
+  while (N < n) N <<= 1;
+  auto cx = [&](uint32_t i, uint32_t j) {
+    if (j < n) {
+      const double a = kd[i], c = kd[j];
+      if (a > c) {
+        kd[i] = c; kd[j] = a;
+        const uint32_t t = iv[i]; iv[i] = iv[j]; iv[j] = t;
+      }
+    }
+  };
+  for (uint32_t size = 2; size <= N; size <<= 1) {
+    const uint32_t hs = size >> 1;
+    for (uint32_t t = lane; t < N / 2; t += 32) {
+      const uint32_t blk = t / hs, r = t - blk * hs;
+      cx(blk * size + r, blk * size + (size - 1 - r));
+    }
+    __syncwarp();
+    for (uint32_t stride = size >> 2; stride > 0; stride >>= 1) {
+      for (uint32_t t = lane; t < N / 2; t += 32) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        cx(i, i + stride);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // Rank every draw of one coarse bucket (n draws, sorted offset B0) exactly.
 // TWO_PASS = false: the bucket is read once into registers (n <= NT * IPT);
 // TWO_PASS = true : any n <= CAP, the bucket is read twice and slots come from cursors.
@@ -423,12 +491,13 @@ template <int NT, int NF, int CAP, int IPT, bool TWO_PASS>
 __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const BucketFn* fn, int cb, uint32_t B0, uint32_t n,
                                               uint32_t M, int p, const BucketBufs& b, const FinishOut& fo) {
   const int tid = threadIdx.x;
-  const double L = (cb == 0) ? fn->lo : fn->sp[cb - 1];
-  const double U = (cb == fn->nb1 - 1) ? fn->hi : fn->sp[cb];
-  double fs = (U > L) ? (double)NF / (U - L) : 0.0;
-  if (!isfinite(fs)) fs = 0.0;
+  // bucket cb = sub-bucket j of coarse bucket c; NF equal-width fine buckets inside it
+  const int nsub = fn->sub, c = cb / nsub;
+  const double jd = (double)(cb - c * nsub);
+  const double L = (c == 0) ? fn->lo : fn->sp[c - 1];
+  const double fs = fn->fsub[c];
   auto fine = [&](double x) -> int {
-    const double t = (x - L) * fs;
+    const double t = ((x - L) * fs - jd) * (double)NF;
     return (t >= 0.0) ? ((t < (double)NF) ? (int)t : NF - 1) : 0;
   };
   for (int i = tid; i < NF; i += NT) sm.fh[i] = 0;
@@ -529,18 +598,18 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
       mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
       mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
     }
+    // distinct values in one fine bucket (a density spike, or the draws beyond the sample's
+    // extremes): sort the bucket in place, then tie runs by binary search
+    if (mn != mx) warp_sort_pairs(sm.kd + a, sm.i2 + a, e - a);
     for (uint32_t s = a + lane; s < e; s += 32) {
       const double k = sm.kd[s];
       uint32_t less = 0, eq = e - a, eqb = s - a;
       if (mn != mx) {
-        less = 0; eq = 0; eqb = 0;
-        for (uint32_t t = a; t < e; ++t) {
-          const double kt = sm.kd[t];
-          less += (kt < k);
-          const bool same = (kt == k);
-          eq += same;
-          eqb += (same && t < s);
-        }
+        uint32_t lo = a, hi = s;          // first position holding k
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sm.kd[mid] < k) lo = mid + 1; else hi = mid; }
+        uint32_t lo2 = s + 1, hi2 = e;    // first position holding a larger value
+        while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (sm.kd[mid] <= k) lo2 = mid + 1; else hi2 = mid; }
+        less = lo - a; eq = lo2 - lo; eqb = s - lo;
       }
       const uint32_t i = B0 + a + less;
       const uint32_t pos = i + eqb;
@@ -552,20 +621,211 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
   }
 }
 
+
+// ================================================================ wide path (long chains)
+// M above ~330k pooled draws: every coarse bucket is cut into `sub` equal-width sub-buckets
+// (up to 8192 buckets per parameter).  Per-chunk counts would cost as much memory as the draws,
+// so the chunk CTAs add their shared-memory histograms to per-parameter totals (k_bhist_w),
+// and k_partition_w reserves a run inside each bucket with one global atomic per (chunk,
+// bucket).  The order inside a bucket then depends on scheduling, the RESULTS do not: k_finish
+// ranks by value, and draws with equal values receive equal scores.
+struct WideSmem {
+  double sp[NB1_MAX];
+  double fsub[NB1_MAX];
+  uint32_t cnt[NBW_MAX];
+  uint16_t lut[NCELL + 2];
+};
+
+__device__ __forceinline__ int wide_of(double x, double lo, double cs, const WideSmem& sm, int sub) {
+  const int c = coarse_of(x, lo, cs, sm.sp, sm.lut);
+  const double lc = (c == 0) ? lo : sm.sp[c - 1];
+  return c * sub + sub_of(x, lc, sm.fsub[c], sub);
+}
+
+__global__ void __launch_bounds__(PART_NT) k_bhist_w(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
+                                                      BucketBufs b) {
+  extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+  WideSmem& sm = *reinterpret_cast<WideSmem*>(wide_smem_raw);
+  __shared__ double red[33 * 2];
+  const int p = blockIdx.y;
+  const uint32_t chunk = blockIdx.x;
+  const BucketFn* fn = b.fn + p;
+  const double* xp = x + (size_t)p * M;
+  const int sub = fn->sub, nbt = fn->nb1 * sub;
+  for (int i = threadIdx.x; i < NB1_MAX; i += PART_NT) { sm.sp[i] = fn->sp[i]; sm.fsub[i] = fn->fsub[i]; }
+  for (int i = threadIdx.x; i < NCELL + 2; i += PART_NT) sm.lut[i] = fn->lut[i];
+  for (int i = threadIdx.x; i < nbt; i += PART_NT) sm.cnt[i] = 0;
+  const double lo = fn->lo, cs = fn->cs, c0 = fn->c0;
+  __syncthreads();
+  const uint32_t base = chunk * CHUNK_P;
+  double s1 = 0.0, s2 = 0.0;
+  bool bad = false;
+#pragma unroll 4
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = base + it * PART_NT + threadIdx.x;
+    if (e < M) {
+      const double v = xp[e];
+      bad |= !is_finite_bits(v);
+      const double d = v - c0;
+      s1 += d;
+      s2 = fma(d, d, s2);
+      atomicAdd(&sm.cnt[wide_of(v, lo, cs, sm, sub)], 1u);
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red[w] = s1; red[33 + w] = s2; }
+  const int anybad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < PART_NT / 32; ++k) { a += red[k]; c += red[33 + k]; }
+    b.spart[((size_t)p * nchunks + chunk) * 2 + 0] = a;
+    b.spart[((size_t)p * nchunks + chunk) * 2 + 1] = c;
+    if (anybad) atomicOr(b.flag, 1);
+  }
+  uint32_t* tot = b.cur + (size_t)p * NBW_MAX;
+  for (int i = threadIdx.x; i < nbt; i += PART_NT) {
+    const uint32_t c = sm.cnt[i];
+    if (c) atomicAdd(&tot[i], c);
+  }
+}
+
+constexpr int BSW_NT = 1024;
+__global__ void __launch_bounds__(BSW_NT) k_bscan_w(uint32_t M, uint32_t nchunks, BucketBufs b) {
+  __shared__ uint32_t wtot[BSW_NT / 32];
+  __shared__ int over;
+  constexpr int PER = NBW_MAX / BSW_NT;
+  const int p = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) over = 0;
+  __syncthreads();
+  uint32_t* cur = b.cur + (size_t)p * NBW_MAX;
+  const int nbt = b.fn[p].nb1 * b.fn[p].sub;
+  uint32_t c[PER], tsum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = t * PER + k;
+    c[k] = (i < nbt) ? cur[i] : 0u;
+    tsum += c[k];
+    if (c[k] > (uint32_t)CAPBIG) {
+      over = 1;
+    } else if (c[k] > (uint32_t)CAP1) {
+      const int slot = atomicAdd(b.nbigb, 1);
+      if (slot < b.biglist_cap) { b.biglist[2 * slot] = p; b.biglist[2 * slot + 1] = i; }
+      else over = 1;
+    }
+  }
+  uint32_t incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint32_t pre = 0;
+  for (int k = 0; k < w; ++k) pre += wtot[k];
+  uint32_t run = pre + incl - tsum;
+  uint32_t* boff = b.boff + (size_t)p * b.bstride;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = t * PER + k;
+    if (i < nbt) { boff[i] = run; cur[i] = run; }
+    run += c[k];
+  }
+  if (t == BSW_NT - 1) boff[nbt] = run;
+  if (t == 0) {
+    double s1 = 0.0, s2 = 0.0;
+    for (uint32_t k = 0; k < nchunks; ++k) {
+      s1 += b.spart[((size_t)p * nchunks + k) * 2 + 0];
+      s2 += b.spart[((size_t)p * nchunks + k) * 2 + 1];
+    }
+    const double dm = (double)M;
+    const double m1 = s1 / dm;
+    b.mean[p] = b.fn[p].c0 + m1;
+    const double var = (s2 - s1 * m1) / dm;
+    b.sd[p] = sqrt(var > 0.0 ? var : 0.0);
+  }
+  __syncthreads();
+  if (t == 0 && over) {
+    b.fallback[p] = 1;
+    b.plist[atomicAdd(b.nfb, 1)] = p;
+  }
+}
+
+__global__ void __launch_bounds__(PART_NT) k_partition_w(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
+                                                          BucketBufs b) {
+  extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+  WideSmem& sm = *reinterpret_cast<WideSmem*>(wide_smem_raw);
+  const int p = blockIdx.y;
+  if (b.fallback[p] || (*b.flag & 1)) return;
+  const uint32_t chunk = blockIdx.x;
+  const BucketFn* fn = b.fn + p;
+  const double* xp = x + (size_t)p * M;
+  const int tid = threadIdx.x;
+  const int sub = fn->sub, nbt = fn->nb1 * sub;
+  for (int i = tid; i < NB1_MAX; i += PART_NT) { sm.sp[i] = fn->sp[i]; sm.fsub[i] = fn->fsub[i]; }
+  for (int i = tid; i < NCELL + 2; i += PART_NT) sm.lut[i] = fn->lut[i];
+  for (int i = tid; i < nbt; i += PART_NT) sm.cnt[i] = 0;
+  const double lo = fn->lo, cs = fn->cs;
+  __syncthreads();
+  const uint32_t base = chunk * CHUNK_P;
+  const uint32_t n = min((uint32_t)CHUNK_P, M - base);
+  double v[PART_IPT];
+  uint32_t r[PART_IPT];
+  uint16_t bk[PART_IPT];
+#pragma unroll
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = it * PART_NT + tid;
+    v[it] = (e < n) ? xp[base + e] : 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = it * PART_NT + tid;
+    if (e < n) {
+      const int c = wide_of(v[it], lo, cs, sm, sub);
+      bk[it] = (uint16_t)c;
+      r[it] = atomicAdd(&sm.cnt[c], 1u);
+    }
+  }
+  __syncthreads();
+  // reserve this chunk's run in every bucket it touches: one global atomic per (chunk, bucket)
+  uint32_t* cur = b.cur + (size_t)p * NBW_MAX;
+  for (int i = tid; i < nbt; i += PART_NT) {
+    const uint32_t c = sm.cnt[i];
+    if (c) sm.cnt[i] = atomicAdd(&cur[i], c);
+  }
+  __syncthreads();
+  uint64_t* ok = b.pkey + (size_t)p * M;
+  uint32_t* oi = b.pidx + (size_t)p * M;
+#pragma unroll
+  for (int it = 0; it < PART_IPT; ++it) {
+    const uint32_t e = it * PART_NT + tid;
+    if (e < n) {
+      const uint32_t pos = sm.cnt[bk[it]] + r[it];
+      ok[pos] = dbl2key(v[it]);
+      oi[pos] = base + e;
+    }
+  }
+}
+
 using FinSmemSmall = FinSmem<CAP1, NFINE>;
 using FinSmemBig = FinSmem<CAPBIG, NFINE_BIG>;
 
 // one CTA per coarse bucket of at most CAP1 draws
-__global__ void __launch_bounds__(FIN_NT, 4) k_finish(uint32_t M, BucketBufs b, FinishOut fo) {
+#ifndef B200REF_FIN_OCC
+#define B200REF_FIN_OCC 6
+#endif
+__global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, BucketBufs b, FinishOut fo) {
   extern __shared__ __align__(16) unsigned char fin_smem_raw[];
   FinSmemSmall& sm = *reinterpret_cast<FinSmemSmall*>(fin_smem_raw);
   const int p = blockIdx.y;
   if (b.fallback[p]) return;
   const int cb = blockIdx.x;
   const BucketFn* fn = b.fn + p;
-  if (cb >= fn->nb1) return;
-  const uint32_t B0 = b.boff[(size_t)p * (NB1_MAX + 1) + cb];
-  const uint32_t n = b.boff[(size_t)p * (NB1_MAX + 1) + cb + 1] - B0;
+  if (cb >= fn->nb1 * fn->sub) return;
+  const uint32_t B0 = b.boff[(size_t)p * b.bstride + cb];
+  const uint32_t n = b.boff[(size_t)p * b.bstride + cb + 1] - B0;
   if (n == 0 || n > (uint32_t)CAP1) return;  // oversize buckets: k_finish_big
   finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, fn, cb, B0, n, M, p, b, fo);
 }
@@ -579,8 +839,8 @@ __global__ void __launch_bounds__(FINB_NT) k_finish_big(uint32_t M, BucketBufs b
   for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
     const int p = b.biglist[2 * q], cb = b.biglist[2 * q + 1];
     if (b.fallback[p]) continue;
-    const uint32_t B0 = b.boff[(size_t)p * (NB1_MAX + 1) + cb];
-    const uint32_t n = b.boff[(size_t)p * (NB1_MAX + 1) + cb + 1] - B0;
+    const uint32_t B0 = b.boff[(size_t)p * b.bstride + cb];
+    const uint32_t n = b.boff[(size_t)p * b.bstride + cb + 1] - B0;
     __syncthreads();
     finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true>(sm, b.fn + p, cb, B0, n, M, p, b, fo);
   }

@@ -105,7 +105,7 @@ inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 // Workspace carve-up for one batch of PB parameters with M pooled draws each.
 struct Layout {
   size_t ztab, zodd, flag, header;  // shared part
-  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
+  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, cur, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
       crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cwl0, cwl1, cnwl, per_batch;
   uint32_t ntiles, nchunks;
   void compute(int64_t PB, int64_t M, bool diag, int64_t C = 1, int64_t N = 1) {
@@ -125,8 +125,10 @@ struct Layout {
     kcode = b; b += up(n * 4);
     zz = b; b += diag ? up(n * 16) : 0;
     fn = b; b += up((size_t)PB * sizeof(BucketFn));
-    cnt = b; b += up((size_t)PB * nchunks * NB1_MAX * 4);
-    boff = b; b += up((size_t)PB * (NB1_MAX + 1) * 4);
+    const bool wide = choose_sub(M) > 1;  // long chains: sub-bucketed coarse buckets, no per-chunk counts
+    cnt = b; b += wide ? 0 : up((size_t)PB * nchunks * NB1_MAX * 4);
+    boff = b; b += up((size_t)PB * (wide ? NBW_MAX + 1 : NB1_MAX + 1) * 4);
+    cur = b; b += wide ? up((size_t)PB * NBW_MAX * 4) : 0;
     spart = b; b += up((size_t)PB * nchunks * 2 * 8);
     fallback = b; b += up((size_t)PB);
     nfb = b; b += up(sizeof(int));
@@ -331,7 +333,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   QuantArgs qa;
   qa.nq = nq;
   for (int i = 0; i < nq; ++i) qa.q[i] = q_host[i];
-  const int nb1 = choose_nb1(M);
+  const int nb1 = choose_nb1(M), nsub = choose_sub(M);
+  const bool wide = nsub > 1;
 
   for (int64_t p0 = 0; p0 < P; p0 += PBmax) {
     const int PB = (int)std::min<int64_t>(PBmax, P - p0);
@@ -340,6 +343,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     bb.fn = (BucketFn*)(wb + L.fn);
     bb.cnt = (uint32_t*)(wb + L.cnt);
     bb.boff = (uint32_t*)(wb + L.boff);
+    bb.bstride = wide ? NBW_MAX + 1 : NB1_MAX + 1;
+    bb.cur = (uint32_t*)(wb + L.cur);
     bb.spart = (double*)(wb + L.spart);
     bb.fallback = (uint8_t*)(wb + L.fallback);
     bb.nfb = (int*)(wb + L.nfb);
@@ -361,8 +366,14 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     // ---- distribution sort: sample -> histogram -> offsets -> partition -> on-chip finish ----
     const dim3 gc(L.nchunks, PB);
     LAUNCH(K_SAMPLE, st, k_sample<<<PB, 512, 0, st>>>(xb, (uint32_t)M, bb));
-    LAUNCH(K_BHIST, st, k_bhist<<<gc, PART_NT, 0, st>>>(xb, (uint32_t)M, L.nchunks, bb));
-    LAUNCH(K_BSCAN, st, k_bscan<<<PB, NB1_MAX, 0, st>>>((uint32_t)M, L.nchunks, bb));
+    if (!wide) {
+      LAUNCH(K_BHIST, st, k_bhist<<<gc, PART_NT, 0, st>>>(xb, (uint32_t)M, L.nchunks, bb));
+      LAUNCH(K_BSCAN, st, k_bscan<<<PB, NB1_MAX, 0, st>>>((uint32_t)M, L.nchunks, bb));
+    } else {
+      CUDA_TRY(cudaMemsetAsync(bb.cur, 0, (size_t)PB * NBW_MAX * 4, st));
+      LAUNCH(K_BHIST, st, k_bhist_w<<<gc, PART_NT, sizeof(WideSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
+      LAUNCH(K_BSCAN, st, k_bscan_w<<<PB, BSW_NT, 0, st>>>((uint32_t)M, L.nchunks, bb));
+    }
 
     // ---- distribution sort, second half (main stream) ----
     // ---- LSD fallback for parameters the bucket function could not balance: a fixed small grid
@@ -407,10 +418,20 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       LAUNCH(K_RANKC, fs, k_rank_codes<<<dim3(L.ntiles, std::min(PB, 8)), RANK_NT, 0, fs>>>(rb, (uint32_t)M, rank_b_batch));
       CUDA_TRY(cudaEventRecord(ss.join, fs));
     }
-    LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
-    LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
+    if (!wide)
+      LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
+    else
+      LAUNCH(K_PARTITION, st, k_partition_w<<<gc, PART_NT, sizeof(WideSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
+    LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1 * nsub, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
     LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
     CUDA_TRY(cudaStreamWaitEvent(st, side_stream().join, 0));
+    if (getenv("B200REF_DEBUG")) {
+      int h[2] = {0, 0};
+      cudaMemcpyAsync(&h[0], bb.nbigb, 4, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(&h[1], bb.nfb, 4, cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "b200ref debug: PB=%d M=%lld nb1=%d sub=%d oversize buckets=%d fallback params=%d\n", PB, (long long)M, nb1, nsub, h[0], h[1]);
+    }
 
     PrepOut po;
     po.quant = (out && out->quantiles) ? out->quantiles + (size_t)p0 * nq : nullptr;

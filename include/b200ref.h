@@ -170,6 +170,18 @@ int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, in
                                double* summary_host /* [P][B200REF_SUMMARY_K] */, uint8_t* passed_host,
                                void* ws_dev, size_t ws_bytes);
 
+/* Ingestion of the reference's long draws table (rows = (chain, draw), one double column per
+ * parameter; store.py:79-95).  Replaces the per-parameter re-bucketing of
+ * convert._chains_from_table (convert.py:150-161):
+ *   row_order:   *flags_host bit0 = some adjacent row pair is out of (chain, draw) order,
+ *                bit1 = an adjacent (chain, draw) pair repeats.  chain / draw are device int64 [rows].
+ *   gather_rows: out[p][r] = in[p][perm[r]] for P parameter columns of M rows (device pointers;
+ *                perm = the row permutation that sorts by (chain, draw)); not in place. */
+int b200ref_row_order_i64(const int64_t* chain_dev, const int64_t* draw_dev, int64_t rows, int* flags_host,
+                          void* stream);
+int b200ref_gather_rows_f64(const double* in_dev, const int64_t* perm_dev, int64_t P, int64_t M, double* out_dev,
+                            void* stream);
+
 /* Batched log-density of the logistic-regression GLM (Stan: y ~ bernoulli_logit(X * beta)):
  *   lp[s] = sum_n ( y[n] * eta - log(1 + exp(eta)) ),  eta = sum_d X[n][d] * beta[s][d]
  * X [N][D], y [N] (0/1), beta [S][D] draws, lp [S]; all fp64 device pointers, row-major.

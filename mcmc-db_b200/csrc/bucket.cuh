@@ -32,7 +32,7 @@ constexpr int NFINE = 512;        // fine buckets per coarse bucket
 constexpr int CAPBIG = 12288;     // oversize coarse buckets up to this many draws: k_finish_big
 constexpr int NFINE_BIG = 2048;
 constexpr int FINB_NT = 1024;
-constexpr int BIGLIST_PER_PARAM = 64;
+constexpr int BIGLIST_PER_PARAM = 256;  // every coarse bucket of a parameter may be oversize (heavy ties)
 constexpr int CAP1 = 2048;        // draws a coarse bucket may hold (on-chip capacity of k_finish)
 constexpr int OVERSAMPLE = 16;    // samples per coarse bucket
 constexpr int CHUNK_P = 4096;     // draws per partition chunk

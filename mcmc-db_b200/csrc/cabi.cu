@@ -18,6 +18,7 @@
 #include "chain.cuh"
 #include "common.cuh"
 #include "glm.cuh"
+#include "ingest.cuh"
 #include "rank.cuh"
 #include "sort.cuh"
 #include "synth.cuh"
@@ -48,11 +49,11 @@ int fail(int code, const char* fmt, ...) {
 // ---- optional per-kernel timing (bench.py's roofline block): CUDA events recorded on the
 // launching stream around every kernel while enabled.
 enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_FINISHB, K_HIST0, K_RADIX, K_RANKC, K_PREP,
-                K_MPART, K_FOLD, K_CHAIN, K_DECIDE, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_GLM_PREP, K_GLM, K_COUNT };
+                K_MPART, K_FOLD, K_CHAIN, K_DECIDE, K_FINALIZE, K_SUMMARY, K_COMPARE, K_CHECKS, K_SYNTH, K_GLM_PREP, K_GLM, K_INGEST, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_sample", "k_bhist", "k_bscan", "k_partition", "k_finish", "k_finish_big",
                                            "k_hist0", "k_radix_pass", "k_rank_codes", "k_param_prep",
                                            "k_merge_partition", "k_fold", "k_moments", "k_decide", "k_finalize",
-                                           "k_summary", "k_compare", "k_checks", "k_synth", "k_glm_prep", "k_glm_logistic"};
+                                           "k_summary", "k_compare", "k_checks", "k_synth", "k_glm_prep", "k_glm_logistic", "k_ingest"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
@@ -755,6 +756,37 @@ int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, in
   cudaStreamDestroy(s_copy);
   cudaStreamDestroy(s_comp);
   return rc;
+}
+
+int b200ref_row_order_i64(const int64_t* chain, const int64_t* draw, int64_t rows, int* flags_host, void* stream) {
+  g_err[0] = 0;
+  if (rows < 0 || !flags_host || (rows > 0 && (!chain || !draw))) return fail(B200REF_ERR_ARG, "bad row_order arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  *flags_host = 0;
+  if (rows < 2) return B200REF_OK;
+  int* dflag = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&dflag, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(dflag, 0, sizeof(int), st));
+  const unsigned blocks = (unsigned)std::min<int64_t>((rows + 255) / 256, 148 * 8);
+  LAUNCH(K_INGEST, st, k_row_order<<<blocks, 256, 0, st>>>(chain, draw, rows, dflag));
+  CUDA_TRY(cudaMemcpyAsync(flags_host, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaFreeAsync(dflag, st));
+  CUDA_TRY(cudaGetLastError());
+  return B200REF_OK;
+}
+
+int b200ref_gather_rows_f64(const double* in, const int64_t* perm, int64_t P, int64_t M, double* out, void* stream) {
+  g_err[0] = 0;
+  if (P < 0 || M < 0 || ((P > 0 && M > 0) && (!in || !perm || !out))) return fail(B200REF_ERR_ARG, "bad gather arguments");
+  if (in == out) return fail(B200REF_ERR_ARG, "gather_rows cannot run in place");
+  if (P == 0 || M == 0) return B200REF_OK;
+  if (P > 65535) return fail(B200REF_ERR_ARG, "gather_rows: at most 65535 parameters per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned bx = (unsigned)std::min<int64_t>((M + 255) / 256, 1024);
+  LAUNCH(K_INGEST, st, k_gather_rows<<<dim3(bx, (unsigned)P), 256, 0, st>>>(in, perm, P, M, out));
+  CUDA_TRY(cudaGetLastError());
+  return B200REF_OK;
 }
 
 int b200ref_synth_fill_f64(double* x, int64_t p0, int64_t P, int64_t C, int64_t N, uint64_t seed, int kind,

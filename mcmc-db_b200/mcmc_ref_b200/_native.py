@@ -24,6 +24,7 @@ EXPORTS = (
     "b200ref_compare_f64", "b200ref_checks_f64",
     "b200ref_full_pass_f64", "b200ref_full_pass_host_f64", "b200ref_synth_fill_f64",
     "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64",
+    "b200ref_row_order_i64", "b200ref_gather_rows_f64",
 )
 
 
@@ -81,6 +82,8 @@ def load() -> C.CDLL:
     lib.b200ref_glm_workspace_bytes.restype = sz
     lib.b200ref_glm_workspace_bytes.argtypes = [i64, i64, i64]
     lib.b200ref_glm_logistic_lp_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, sz, vp]
+    lib.b200ref_row_order_i64.argtypes = [vp, vp, i64, C.POINTER(C.c_int), vp]
+    lib.b200ref_gather_rows_f64.argtypes = [vp, vp, i64, i64, vp, vp]
     for name in EXPORTS:  # every symbol include/b200ref.h declares must be exported
         getattr(lib, name)
     _lib = lib

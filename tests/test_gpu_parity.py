@@ -419,3 +419,102 @@ def test_full_size_properties_c2(B):
         want = O.diagnostics_param(x[i].cpu().numpy())
         for k in ("rhat", "ess_bulk", "ess_tail"):
             assert close(float(d[k][i].item()), want[k], TOL), (i, k)
+
+
+# ---------------------------------------------------------------- ingestion, convert gate, CLI
+
+def _table_from(x: np.ndarray, names):
+    import pyarrow as pa
+
+    p, c, n = x.shape
+    cols = {"chain": np.repeat(np.arange(c, dtype=np.int32), n), "draw": np.tile(np.arange(n, dtype=np.int32), c)}
+    for i, name in enumerate(names):
+        cols[name] = x[i].reshape(-1)
+    return pa.table(cols)
+
+
+def test_ingest_orders_rows_on_device(B):
+    from mcmc_ref_b200 import ingest
+
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 4, 257))
+    names = ["a", "b[1]", "b[2]"]
+    table = _table_from(x, names)
+    got, c, n = ingest.table_to_device(table, names)
+    assert (c, n) == (4, 257) and np.array_equal(got.cpu().numpy(), x)
+    shuffled = table.take(rng.permutation(table.num_rows))
+    got2, _, _ = ingest.table_to_device(shuffled, ["b[2]", "a"])
+    assert np.array_equal(got2.cpu().numpy(), x[[2, 0]])
+    import torch
+
+    dev = got.device
+    ch = torch.from_numpy(np.array([0, 0, 1, 1], dtype=np.int64)).to(dev)
+    assert ingest.rows_in_order(ch, torch.tensor([0, 1, 0, 1], device=dev)) == (True, False)
+    assert ingest.rows_in_order(ch, torch.tensor([1, 0, 0, 1], device=dev)) == (False, False)
+    assert ingest.rows_in_order(ch, torch.tensor([0, 0, 0, 1], device=dev)) == (True, True)
+
+
+def test_convert_gate_reproduces_shipped_meta(B, packaged_subset, tmp_path):
+    """convert_table on the packaged draws gives the meta.json the reference shipped (convert.py:44-66)."""
+    from mcmc_ref_b200 import convert
+
+    arrays, meta = packaged_subset
+    for model, info in meta.items():
+        table = _table_from(arrays[model], info["params"])
+        res = convert.convert_table(table, model, tmp_path, tmp_path, force=True)
+        m = res.meta
+        assert m["parameters"] == info["params"] and m["n_chains"] == info["n_chains"]
+        assert m["n_draws_per_chain"] == info["n_draws_per_chain"] and m["checks"] == info["checks"]
+        assert set(m) == {"model", "parameters", "n_chains", "n_draws_per_chain", "diagnostics", "generated_date",
+                          "checks", "source"}
+        for p in info["params"]:
+            for k in ("rhat", "ess_bulk", "ess_tail"):
+                assert close(m["diagnostics"][p][k], info["diagnostics"][p][k], TOL), (model, p, k)
+        import json
+
+        assert json.loads(res.meta_path.read_text())["diagnostics"].keys() == m["diagnostics"].keys()
+        assert res.draws_path.exists()
+    few = _table_from(np.random.default_rng(0).standard_normal((1, 2, 50)), ["mu"])
+    with pytest.raises(ValueError, match="at least 4 chains"):
+        convert.convert_table(few, "few")
+    bad = _table_from(np.random.default_rng(0).standard_normal((1, 4, 50)), ["mu"])
+    with pytest.raises(ValueError, match="quality checks failed: ndraws_is_10k"):
+        convert.convert_table(bad, "bad")
+
+
+def test_cli_hot_path_commands(B, tmp_path, monkeypatch):
+    """The reference's CLI tests (tests/unit/test_cli.py:41-86) through the b200 commands."""
+    import json
+
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from click.testing import CliRunner
+
+    from mcmc_ref_b200.cli import main
+
+    (tmp_path / "draws").mkdir()
+    (tmp_path / "meta").mkdir()
+    pq.write_table(pa.table({
+        "chain": pa.array([0, 0, 1, 1, 2, 2, 3, 3], type=pa.int32()),
+        "draw": pa.array([0, 1, 0, 1, 0, 1, 0, 1], type=pa.int32()),
+        "mu": pa.array([1.0, 2.0, 1.5, 2.5, 1.0, 2.0, 1.5, 2.5], type=pa.float64()),
+    }), tmp_path / "draws" / "example.draws.parquet")
+    (tmp_path / "meta" / "example.meta.json").write_text("{}")
+    monkeypatch.setenv("MCMC_REF_LOCAL_ROOT", str(tmp_path))
+    runner = CliRunner()
+    res = runner.invoke(main, ["stats", "example", "--format", "json", "--include-diagnostics", "--quantile-mode", "exact"])
+    assert res.exit_code == 0, res.output
+    out = json.loads(res.output)
+    assert out["mu"]["mean"] == 1.75 and out["mu"]["std"] == 0.5590169943749475
+    assert math.isnan(out["mu"]["rhat"]) and out["mu"]["ess_bulk"] == 8.0  # the reference's values for this fixture
+    actual = tmp_path / "actual.csv"
+    actual.write_text("chain,draw,mu\n0,0,1.0\n0,1,2.0\n1,0,1.5\n1,1,2.5\n")
+    res = runner.invoke(main, ["compare", "example", "--actual", str(actual)])
+    assert res.exit_code == 0 and "passed" in res.output
+    actual.write_text("chain,draw,mu\n0,0,10.0\n0,1,20.0\n")
+    res = runner.invoke(main, ["compare", "example", "--actual", str(actual), "--format", "json"])
+    assert res.exit_code == 2
+    body = json.loads(res.output)
+    assert body["passed"] is False and body["failures"][0].startswith("mu.mean rel_error=")
+    res = runner.invoke(main, ["diagnostics", "example", "--format", "csv", "--recompute"])
+    assert res.exit_code == 0 and res.output.splitlines()[0] == "param,rhat,ess_bulk,ess_tail"

@@ -237,13 +237,17 @@ struct FoldOut {
   double* rankf;
 };
 
+// Index into the folded-bits window: one pad word per 4 keeps the merge's reads (neighbouring threads
+// walk the windows ~4 elements apart) off the same shared-memory banks.
+__device__ __forceinline__ uint32_t sdi(uint32_t i) { return i + (i >> 2); }
+
 // One CTA = RANK_TILE consecutive outputs of the folded (merged) order.
 //  phase 1  every global read of the tile is issued up front and coalesced: the left / right
 //           windows of the sorted sequence (keys -> folded bits, original positions, bulk tie codes);
 //  phase 2  per-thread merge path + serial merge in shared memory, tie detection (rare path: tie codes);
 //  phase 3  striped over the outputs: two table lookups and ONE 16-byte scatter per draw.
 __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
-  __shared__ uint64_t sd[RANK_TILE];      // left window then right window (folded bits); later: tie codes
+  __shared__ uint64_t sd[RANK_TILE + RANK_TILE / 4 + 2];  // left window then right window (folded bits, index sdi()); later: tie codes
   __shared__ uint32_t sp[RANK_TILE];      // original positions of the window elements
   __shared__ double szb[RANK_TILE];       // bulk scores of the window elements
   __shared__ uint16_t ssrc[RANK_TILE];    // merged output -> window slot
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, ui
 #pragma unroll
     for (int j = 0; j < HB; ++j) {
       const uint32_t e = min((h * HB + j) * RANK_NT + threadIdx.x, n - 1);
-      sd[e] = (uint64_t)__double_as_longlong(fabs(__dsub_rn(key2dbl(kv[j]), f.med)));
+      sd[sdi(e)] = (uint64_t)__double_as_longlong(fabs(__dsub_rn(key2dbl(kv[j]), f.med)));
       sp[e] = pi[j];
       szb[e] = zo[j];
     }
@@ -318,38 +322,45 @@ __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, ui
   }
   __syncthreads();
 
-  // per-thread merge path inside the tile
+  // per-thread merge path inside the tile; ties (continuous draws: almost never) are detected on
+  // the fly by comparing each output with its predecessor
+  bool tie = false;
   {
     const uint32_t od = min((uint32_t)threadIdx.x * RANK_IPT, n);
     uint32_t lo = (od > nr) ? od - nr : 0, hi = min(od, nl);
     while (lo < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (sd[mid] <= sd[nl + od - 1 - mid]) lo = mid + 1; else hi = mid;
+      if (sd[sdi(mid)] <= sd[sdi(nl + od - 1 - mid)]) lo = mid + 1; else hi = mid;
     }
     uint32_t la = lo, lc = od - lo;
-    uint64_t vl = (la < nl) ? sd[la] : ~0ull, vr = (lc < nr) ? sd[nl + lc] : ~0ull;
+    uint64_t vl = (la < nl) ? sd[sdi(la)] : ~0ull, vr = (lc < nr) ? sd[sdi(nl + lc)] : ~0ull;
+    // merged value just before this thread's first output
+    uint64_t prev = 0;
+    bool have_prev = has_prev;
+    if (od == 0) {
+      prev = sv[0];
+    } else {
+      if (la > 0) prev = sd[sdi(la - 1)];
+      if (lc > 0) prev = max(prev, sd[sdi(nl + lc - 1)]);
+      have_prev = true;
+    }
 #pragma unroll
     for (int it = 0; it < RANK_IPT; ++it) {
       const uint32_t e = od + it;
       if (e < n) {
         const bool takeL = (la < nl) && (lc >= nr || vl <= vr);
-        sv[pidx8(e + 1)] = takeL ? vl : vr;
+        const uint64_t v = takeL ? vl : vr;
+        tie |= have_prev && (v == prev);
+        prev = v;
+        have_prev = true;
+        sv[pidx8(e + 1)] = v;
         ssrc[e] = (uint16_t)(takeL ? la : nl + lc);
-        if (takeL) { ++la; vl = (la < nl) ? sd[la] : ~0ull; }
-        else       { ++lc; vr = (lc < nr) ? sd[nl + lc] : ~0ull; }
+        if (takeL) { ++la; vl = (la < nl) ? sd[sdi(la)] : ~0ull; }
+        else       { ++lc; vr = (lc < nr) ? sd[sdi(nl + lc)] : ~0ull; }
+        if (e == n - 1) tie |= has_next && (sv[pidx8(n + 1)] == v);
       }
     }
   }
-  __syncthreads();
-
-  // any tie in this tile (or across its edges)?  Continuous draws: almost never.
-  bool tie = false;
-#pragma unroll
-  for (int it = 0; it < RANK_IPT; ++it) {
-    const uint32_t e = threadIdx.x * RANK_IPT + it;
-    if (e + 1 < n) tie |= (sv[pidx8(e + 1)] == sv[pidx8(e + 2)]);
-  }
-  if (threadIdx.x == 0) tie |= (has_prev && sv[0] == sv[pidx8(1)]) || (has_next && sv[pidx8(n + 1)] == sv[pidx8(n)]);
   const int any_tie = __syncthreads_or(tie);
   uint32_t* sk = reinterpret_cast<uint32_t*>(sd);  // sd is dead after the merge: reuse for k codes
   if (any_tie) {

@@ -159,7 +159,10 @@ int b200ref_checks_f64(const double* rhat_dev, const double* ess_bulk_dev, int64
 #define B200REF_S_Z_MEAN 18
 #define B200REF_S_Z_PASS 19
 
-/* Device-resident form: inputs already in HBM, summary written to device. */
+/* Device-resident form: inputs already in HBM, summary written to device.  With a workspace of
+ * b200ref_full_pass_workspace_bytes() the statistics of the reference draws run on an auxiliary
+ * stream underneath the candidate pass; with less they run after it (same results). */
+size_t b200ref_full_pass_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t Mref);
 int b200ref_full_pass_f64(const double* cand_dev, int64_t P, int64_t C, int64_t N,
                           const double* ref_dev, int64_t Mref, double tol, double z_crit,
                           double* summary_dev /* [P][B200REF_SUMMARY_K] */, uint8_t* passed_host,

@@ -90,8 +90,9 @@ struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-SideStream& side_stream() {
-  thread_local SideStream ss;
+SideStream& side_stream(int slot = 0) {
+  thread_local SideStream pool[2];
+  SideStream& ss = pool[slot & 1];
   if (!ss.s) {
     cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
@@ -298,7 +299,7 @@ struct Mode {
 // Process P parameters in batches.  `x` [P][M]; outputs are offset per batch.
 int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, int nq, const b200ref_outputs* out,
         double* rank_b, double* z_b, double* rank_f, double* z_f, Mode mode, void* ws, size_t ws_bytes,
-        cudaStream_t st) {
+        cudaStream_t st, int slot = 0, int** deferred_flag = nullptr) {
   const int64_t M = C * N;
   if (!x || P < 0 || C < 1 || N < 1) return fail(B200REF_ERR_ARG, "bad shape P=%lld C=%lld N=%lld", (long long)P,
                                                  (long long)C, (long long)N);
@@ -407,7 +408,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     {
       // while per-kernel timing is on, the fallback runs on the main stream so that every
       // event pair brackets one kernel alone (overlapped launches would share their interval)
-      SideStream& ss = side_stream();
+      SideStream& ss = side_stream(slot);
       cudaStream_t fs = g_prof ? st : ss.s;
       CUDA_TRY(cudaEventRecord(ss.fork, st));
       CUDA_TRY(cudaStreamWaitEvent(fs, ss.fork, 0));
@@ -425,7 +426,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       LAUNCH(K_PARTITION, st, k_partition_w<<<gc, PART_NT, sizeof(WideSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
     LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1 * nsub, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
     LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
-    CUDA_TRY(cudaStreamWaitEvent(st, side_stream().join, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, side_stream(slot).join, 0));
     if (getenv("B200REF_DEBUG")) {
       int h[2] = {0, 0};
       cudaMemcpyAsync(&h[0], bb.nbigb, 4, cudaMemcpyDeviceToHost, st);
@@ -508,6 +509,10 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     }
   }
   CUDA_TRY(cudaGetLastError());
+  if (deferred_flag) {  // the caller joins the stream and reads the flag itself
+    *deferred_flag = flag;
+    return B200REF_OK;
+  }
   int hflag = 0;
   CUDA_TRY(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -639,7 +644,30 @@ int b200ref_checks_f64(const double* rhat, const double* essb, int64_t P, uint8_
 
 // Scratch for the fused pass, carved from the END of the workspace:
 //   per-parameter result columns (13 doubles) + nfail.
+// workspace of the (non-diagnostic) statistics pass over the reference draws of P parameters
+static size_t ref_workspace_bytes(int64_t P, int64_t Mref) {
+  Layout l;
+  l.compute(std::min<int64_t>(std::max<int64_t>(P, 1), BATCH_CAP), Mref, false);
+  return l.header + l.per_batch;
+}
+struct AuxStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxStream& aux_stream() {
+  thread_local AuxStream ax;
+  if (!ax.s) {
+    cudaStreamCreateWithFlags(&ax.s, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ax.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ax.join, cudaEventDisableTiming);
+  }
+  return ax;
+}
 static size_t fused_tail_bytes(int64_t P) { return up((size_t)P * 13 * 8) + up(16); }
+
+size_t b200ref_full_pass_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t Mref) {
+  return b200ref_workspace_bytes(P, C, N) + ref_workspace_bytes(P, Mref) + fused_tail_bytes(std::max<int64_t>(P, 1)) + 4 * ALIGN;
+}
 
 int b200ref_full_pass_f64(const double* cand, int64_t P, int64_t C, int64_t N, const double* ref, int64_t Mref,
                           double tol, double z_crit, double* summary, uint8_t* passed_host, void* ws,
@@ -658,13 +686,38 @@ int b200ref_full_pass_f64(const double* cand, int64_t P, int64_t C, int64_t N, c
   b200ref_outputs oc;
   memset(&oc, 0, sizeof(oc));
   oc.rhat = rhat; oc.ess_bulk = essb; oc.ess_tail = esst; oc.mean = mean; oc.std = sd; oc.quantiles = q;
-  int rc = run(cand, P, C, N, qs, 3, &oc, nullptr, nullptr, nullptr, nullptr, Mode{true, false}, ws, body, st);
-  if (rc) return rc;
   b200ref_outputs orf;
   memset(&orf, 0, sizeof(orf));
   orf.mean = rmean; orf.std = rsd; orf.quantiles = rq;
-  rc = run(ref, P, 1, Mref, qs, 3, &orf, nullptr, nullptr, nullptr, nullptr, Mode{false, false}, ws, body, st);
-  if (rc) return rc;
+  // The reference-draw statistics are independent of the candidate pass: when the workspace has
+  // room for both, they run on an auxiliary stream underneath it (small, latency-bound launches).
+  const size_t ref_need = ref_workspace_bytes(P, Mref);
+  const bool overlap = !g_prof && ref_need <= body / 4;
+  int rc;
+  if (overlap) {
+    AuxStream& ax = aux_stream();
+    char* ref_ws = (char*)ws + (body - ref_need) / ALIGN * ALIGN;
+    const size_t cand_body = (size_t)(ref_ws - (char*)ws);
+    int* ref_flag = nullptr;
+    CUDA_TRY(cudaEventRecord(ax.fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(ax.s, ax.fork, 0));
+    rc = run(ref, P, 1, Mref, qs, 3, &orf, nullptr, nullptr, nullptr, nullptr, Mode{false, false}, ref_ws, ref_need,
+             ax.s, 1, &ref_flag);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ax.join, ax.s));
+    rc = run(cand, P, C, N, qs, 3, &oc, nullptr, nullptr, nullptr, nullptr, Mode{true, false}, ws, cand_body, st);
+    CUDA_TRY(cudaStreamWaitEvent(st, ax.join, 0));  // also on an error return path below: the aux work is always joined
+    int hflag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hflag, ref_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (rc) return rc;
+    if (hflag & 1) return fail(B200REF_ERR_NONFINITE, "non-finite value (NaN or inf) in input draws");
+  } else {
+    rc = run(cand, P, C, N, qs, 3, &oc, nullptr, nullptr, nullptr, nullptr, Mode{true, false}, ws, body, st);
+    if (rc) return rc;
+    rc = run(ref, P, 1, Mref, qs, 3, &orf, nullptr, nullptr, nullptr, nullptr, Mode{false, false}, ws, body, st);
+    if (rc) return rc;
+  }
   CUDA_TRY(cudaMemsetAsync(nfail, 0, sizeof(int), st));
   LAUNCH(K_SUMMARY, st, k_summary<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(rhat, essb, esst, mean, sd, q, rmean, rsd, rq, tol, z_crit,
                                                          Mref, P, summary, nfail));
@@ -696,7 +749,7 @@ int b200ref_full_pass_host_f64(const double* cand_host, int64_t P, int64_t C, in
   int64_t slab = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t)(slab_bytes / per_param_in)));
   size_t need = 0;
   for (; slab >= 1; slab = (slab > 1) ? slab / 2 : 0) {
-    need = 2 * up(per_param_in * slab) + b200ref_workspace_bytes(slab, C, N) + fused_tail_bytes(slab) + ALIGN;
+    need = 2 * up(per_param_in * slab) + b200ref_full_pass_workspace_bytes(slab, C, N, Mref) + ALIGN;
     if (need <= ws_bytes) break;
   }
   int rc = B200REF_OK;

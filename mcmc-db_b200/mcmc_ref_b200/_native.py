@@ -22,7 +22,7 @@ EXPORTS = (
     "b200ref_workspace_bytes", "b200ref_workspace_min_bytes",
     "b200ref_ranks_f64", "b200ref_diagnostics_f64", "b200ref_stats_f64",
     "b200ref_compare_f64", "b200ref_checks_f64",
-    "b200ref_full_pass_f64", "b200ref_full_pass_host_f64", "b200ref_synth_fill_f64",
+    "b200ref_full_pass_workspace_bytes", "b200ref_full_pass_f64", "b200ref_full_pass_host_f64", "b200ref_synth_fill_f64",
     "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64",
     "b200ref_row_order_i64", "b200ref_gather_rows_f64",
 )
@@ -76,6 +76,8 @@ def load() -> C.CDLL:
     lib.b200ref_stats_f64.argtypes = [vp, i64, i64, C.POINTER(dbl), C.c_int, C.POINTER(Outputs), vp, sz, vp]
     lib.b200ref_compare_f64.argtypes = [vp, vp, i64, dbl, vp, vp, vp, vp]
     lib.b200ref_checks_f64.argtypes = [vp, vp, i64, C.POINTER(C.c_uint8), vp]
+    lib.b200ref_full_pass_workspace_bytes.restype = sz
+    lib.b200ref_full_pass_workspace_bytes.argtypes = [i64, i64, i64, i64]
     lib.b200ref_full_pass_f64.argtypes = [vp, i64, i64, i64, vp, i64, dbl, dbl, vp, C.POINTER(C.c_uint8), vp, sz, vp]
     lib.b200ref_full_pass_host_f64.argtypes = [vp, i64, i64, i64, vp, i64, dbl, dbl, vp, C.POINTER(C.c_uint8), vp, sz]
     lib.b200ref_synth_fill_f64.argtypes = [vp, i64, i64, i64, i64, u64, C.c_int, vp]

@@ -190,7 +190,9 @@ def full_pass(cand, ref, tolerance: float = 0.15, workspace: Workspace | None = 
     p, c, n = ct.shape
     rt = rt.reshape(p, -1)
     summary = torch.empty((p, _native.SUMMARY_K), dtype=torch.float64, device=ct.device)
-    ws = (workspace or _WS).for_shape(p, c, n, extra=p * 13 * 8 + 1024, cap_bytes=ws_cap_bytes)
+    # room for the reference-draw statistics to run underneath the candidate pass (aux stream)
+    extra = int(lib.b200ref_full_pass_workspace_bytes(p, c, n, rt.shape[1])) - int(lib.b200ref_workspace_bytes(p, c, n))
+    ws = (workspace or _WS).for_shape(p, c, n, extra=extra, cap_bytes=ws_cap_bytes)
     ok = C.c_uint8(0)
     _native.check(lib.b200ref_full_pass_f64(ct.data_ptr(), p, c, n, rt.data_ptr(), rt.shape[1], float(tolerance),
                                             float(z_crit), summary.data_ptr(), C.byref(ok), ws.data_ptr(), ws.numel(),
@@ -218,8 +220,8 @@ def full_pass_host(cand_host: torch.Tensor, ref_host: torch.Tensor, tolerance: f
         summary_host = torch.empty((p, _native.SUMMARY_K), dtype=torch.float64, pin_memory=True)
     if ws_bytes is None:
         slab = min(p, 1024)
-        ws_bytes = (int(lib.b200ref_workspace_bytes(slab, c, n)) + 2 * slab * (c * n + mref + _native.SUMMARY_K) * 8
-                    + slab * 13 * 8 + 8192)
+        ws_bytes = (int(lib.b200ref_full_pass_workspace_bytes(slab, c, n, mref))
+                    + 2 * slab * (c * n + mref + _native.SUMMARY_K) * 8 + 8192)
     ws = (workspace or _WS).ensure(ws_bytes)
     ok = C.c_uint8(0)
     _native.check(lib.b200ref_full_pass_host_f64(cand_host.data_ptr(), p, c, n, ref_host.data_ptr(), mref,

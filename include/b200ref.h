@@ -103,6 +103,19 @@ int b200ref_diagnostics_f64(const double* x_dev, int64_t P, int64_t C, int64_t N
                             const double* q_host, int nq, const b200ref_outputs* out,
                             void* ws_dev, size_t ws_bytes, void* stream);
 
+/* Same, with the truncation rule of the ESS autocorrelation sum selectable.
+ *   B200REF_ESS_FIRST_NEGATIVE  the reference's rule (diagnostics.py:172-176): stop at the first rho_t < 0
+ *   B200REF_ESS_GEYER           EXTENSION, not in the reference: Geyer's initial monotone sequence on
+ *                               the same rho_t (rho_0 := 1, pairs rho_2k + rho_2k+1, stop before the
+ *                               first negative pair, pairs capped by their predecessor,
+ *                               ESS = m n / max(-1 + 2 sum of pairs, 1 / log10(m n))); defined by the oracle,
+ *                               parity unpinned. */
+#define B200REF_ESS_FIRST_NEGATIVE 0
+#define B200REF_ESS_GEYER 1
+int b200ref_diagnostics_ex_f64(const double* x_dev, int64_t P, int64_t C, int64_t N,
+                               const double* q_host, int nq, int ess_mode, const b200ref_outputs* out,
+                               void* ws_dev, size_t ws_bytes, void* stream);
+
 /* mean / std(ddof=0) / numpy-linear quantiles over the pooled M draws of each of
  * P parameters; no diagnostics.  Replaces NumpyBackend.stats (backends_numpy.py:17-49).
  * Only out->mean, std, quantiles, order_stats, median are written. */

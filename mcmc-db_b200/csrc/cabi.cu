@@ -108,7 +108,7 @@ inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 struct Layout {
   size_t ztab, zodd, flag, header;  // shared part
   size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, cur, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
-      crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cwl0, cwl1, cnwl, per_batch;
+      crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cgpend, cgprev, cwl0, cwl1, cnwl, per_batch;
   uint32_t ntiles, nchunks;
   void compute(int64_t PB, int64_t M, bool diag, int64_t C = 1, int64_t N = 1) {
     ntiles = (uint32_t)((M + RANK_TILE - 1) / RANK_TILE);
@@ -159,6 +159,8 @@ struct Layout {
       ctail = b; b += up((size_t)2 * PB * C * 8);
       cvarhat = b; b += up((size_t)2 * PB * 8);
       crhosum = b; b += up((size_t)2 * PB * 8);
+      cgpend = b; b += up((size_t)2 * PB * 8);
+      cgprev = b; b += up((size_t)2 * PB * 8);
       cwl0 = b; b += up((size_t)2 * PB * 4);
       cwl1 = b; b += up((size_t)2 * PB * 4);
       cnwl = b; b += up(2 * sizeof(int));
@@ -294,6 +296,7 @@ __global__ void k_summary(const double* rhat, const double* essb, const double* 
 struct Mode {
   bool diag;         // run fold + chain kernels
   bool want_ranks;   // scatter average ranks (ranks API)
+  bool geyer = false;  // extension: Geyer initial-monotone ESS truncation instead of the reference's first-negative rule
 };
 
 // Process P parameters in batches.  `x` [P][M]; outputs are offset per batch.
@@ -467,6 +470,9 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       cs.tail = (double*)(wb + L.ctail);
       cs.varhat = (double*)(wb + L.cvarhat);
       cs.rhosum = (double*)(wb + L.crhosum);
+      cs.gpend = (double*)(wb + L.cgpend);
+      cs.gprev = (double*)(wb + L.cgprev);
+      cs.geyer = mode.geyer ? 1 : 0;
       cs.wl[0] = (int*)(wb + L.cwl0);
       cs.wl[1] = (int*)(wb + L.cwl1);
       cs.nwl = (int*)(wb + L.cnwl);
@@ -585,6 +591,18 @@ int b200ref_diagnostics_f64(const double* x, int64_t P, int64_t C, int64_t N, co
   if (!out) return fail(B200REF_ERR_ARG, "null outputs");
   if (nq > 0 && !q_host) return fail(B200REF_ERR_ARG, "null quantile levels");
   Mode m{true, false};
+  return run(x, P, C, N, q_host, nq, out, nullptr, nullptr, nullptr, nullptr, m, ws, ws_bytes,
+             (cudaStream_t)stream);
+}
+
+int b200ref_diagnostics_ex_f64(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, int nq,
+                               int ess_mode, const b200ref_outputs* out, void* ws, size_t ws_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!out) return fail(B200REF_ERR_ARG, "null outputs");
+  if (nq > 0 && !q_host) return fail(B200REF_ERR_ARG, "null quantile levels");
+  if (ess_mode != B200REF_ESS_FIRST_NEGATIVE && ess_mode != B200REF_ESS_GEYER)
+    return fail(B200REF_ERR_ARG, "unknown ess_mode %d", ess_mode);
+  Mode m{true, false, ess_mode == B200REF_ESS_GEYER};
   return run(x, P, C, N, q_host, nq, out, nullptr, nullptr, nullptr, nullptr, m, ws, ws_bytes,
              (cudaStream_t)stream);
 }

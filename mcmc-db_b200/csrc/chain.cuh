@@ -95,6 +95,9 @@ struct ChainState {
   double* tail;      // [2*PB][C]  sum of the last  (t0 - 1) draws
   double* varhat;    // [2*PB]
   double* rhosum;    // [2*PB]
+  double* gpend;     // [2*PB] Geyer mode: first correlation of the open pair (NaN: none pending)
+  double* gprev;     // [2*PB] Geyer mode: previous (capped) pair sum
+  int geyer;         // 0 = the reference's first-negative truncation, 1 = Geyer initial monotone sequence (extension)
   int* wl[2];        // work lists of unfinished items (2*p + kind)
   int* nwl;          // [2] their lengths
   double* rhat;      // [2][PB] outputs, kind-major
@@ -371,7 +374,36 @@ __device__ __forceinline__ bool rho_walk(const double* lagsum, int nl, uint32_t 
     if (rho < 0.0) { lag_out = (long long)t; return true; }
     rho_sum += rho;
   }
-  return false;
+  return t0 + (uint32_t)nl >= N;  // no lag left for another round
+}
+
+// ESS = m n / max(-1 + 2 sum of pairs, 1 / log10(m n))
+__device__ __forceinline__ double geyer_ess(double mn, double pair_sum) {
+  const double tau = -1.0 + 2.0 * pair_sum, floor_tau = 1.0 / log10(mn);
+  return mn / ((tau > floor_tau) ? tau : floor_tau);
+}
+
+// EXTENSION (not in the reference): Geyer's initial monotone sequence on the same rho_t, rho_0 := 1.
+// Pairs P_k = rho_2k + rho_2k+1; stop before the first negative pair, cap every pair by its
+// predecessor; only complete pairs count.  `pend` carries the open pair's first term across rounds.
+__device__ __forceinline__ bool geyer_walk(const double* lagsum, int nl, uint32_t t0, uint32_t N, uint32_t C, double varhat,
+                                           double& pair_sum, double& pend, double& prev, long long& lag_out) {
+  const double mv = (double)C * varhat;
+  for (int l = 0; l < nl; ++l) {
+    const uint32_t t = t0 + l;
+    if (t >= N) return true;
+    const double rho = (lagsum[l] / (double)(N - t)) / mv;
+    if (t & 1u) {  // odd lag closes the pair opened by rho_{t-1}
+      double pair = pend + rho;
+      if (pair < 0.0) { lag_out = (long long)(t - 1); return true; }
+      pair = (pair < prev) ? pair : prev;
+      pair_sum += pair;
+      prev = pair;
+    } else {
+      pend = rho;
+    }
+  }
+  return t0 + (uint32_t)nl >= N;  // no lag left for another round (an open pair is dropped)
 }
 
 // ---------------------------------------------------------------- round 0 decision: R-hat, var_hat, lags 1..16
@@ -482,13 +514,27 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
       } else {
         double rho_sum = 0.0;
         long long lag = (long long)N;
-        if (rho_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, lag)) {
-          st.ess[o] = (double)C * dn / (1.0 + 2.0 * rho_sum);
-          st.lag[o] = lag;
+        if (!st.geyer) {
+          if (rho_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, lag)) {
+            st.ess[o] = (double)C * dn / (1.0 + 2.0 * rho_sum);
+            st.lag[o] = lag;
+          } else {
+            st.varhat[item] = var_hat;
+            st.rhosum[item] = rho_sum;
+            st.wl[0][atomicAdd(&st.nwl[0], 1)] = item;
+          }
         } else {
-          st.varhat[item] = var_hat;
-          st.rhosum[item] = rho_sum;
-          st.wl[0][atomicAdd(&st.nwl[0], 1)] = item;
+          double pend = 1.0, prev = inf;  // rho_0 := 1 opens the first pair
+          if (geyer_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, pend, prev, lag)) {
+            st.ess[o] = geyer_ess((double)C * dn, rho_sum);
+            st.lag[o] = lag;
+          } else {
+            st.varhat[item] = var_hat;
+            st.rhosum[item] = rho_sum;
+            st.gpend[item] = pend;
+            st.gprev[item] = prev;
+            st.wl[0][atomicAdd(&st.nwl[0], 1)] = item;
+          }
         }
       }
     }
@@ -529,12 +575,25 @@ __global__ void __launch_bounds__(DEC_NT) k_decide_r(const double2* __restrict__
     const size_t o = (size_t)kind * PB + p;
     double rho_sum = st.rhosum[item];
     long long lag = (long long)N;
-    if (rho_walk(tot, LAGR, t0, N, C, st.varhat[item], rho_sum, lag)) {
-      st.ess[o] = (double)C * (double)N / (1.0 + 2.0 * rho_sum);
-      st.lag[o] = lag;
+    if (!st.geyer) {
+      if (rho_walk(tot, LAGR, t0, N, C, st.varhat[item], rho_sum, lag)) {
+        st.ess[o] = (double)C * (double)N / (1.0 + 2.0 * rho_sum);
+        st.lag[o] = lag;
+      } else {
+        st.rhosum[item] = rho_sum;
+        st.wl[cur ^ 1][atomicAdd(&st.nwl[cur ^ 1], 1)] = item;
+      }
     } else {
-      st.rhosum[item] = rho_sum;
-      st.wl[cur ^ 1][atomicAdd(&st.nwl[cur ^ 1], 1)] = item;
+      double pend = st.gpend[item], prev = st.gprev[item];
+      if (geyer_walk(tot, LAGR, t0, N, C, st.varhat[item], rho_sum, pend, prev, lag)) {
+        st.ess[o] = geyer_ess((double)C * (double)N, rho_sum);
+        st.lag[o] = lag;
+      } else {
+        st.rhosum[item] = rho_sum;
+        st.gpend[item] = pend;
+        st.gprev[item] = prev;
+        st.wl[cur ^ 1][atomicAdd(&st.nwl[cur ^ 1], 1)] = item;
+      }
     }
   }
 }

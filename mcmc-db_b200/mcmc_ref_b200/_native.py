@@ -15,12 +15,13 @@ _LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libb200ref.so"
 ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_NONFINITE = -1, -2, -3, -4
 SUMMARY_K = 20
 MAX_QUANTILES = 8
+ESS_MODES = {"first_negative": 0, "geyer": 1}
 
 EXPORTS = (
     "b200ref_version", "b200ref_last_error", "b200ref_kernel_launches",
     "b200ref_profile", "b200ref_profile_read", "b200ref_profile_name",
     "b200ref_workspace_bytes", "b200ref_workspace_min_bytes",
-    "b200ref_ranks_f64", "b200ref_diagnostics_f64", "b200ref_stats_f64",
+    "b200ref_ranks_f64", "b200ref_diagnostics_f64", "b200ref_diagnostics_ex_f64", "b200ref_stats_f64",
     "b200ref_compare_f64", "b200ref_checks_f64",
     "b200ref_full_pass_workspace_bytes", "b200ref_full_pass_f64", "b200ref_full_pass_host_f64", "b200ref_synth_fill_f64",
     "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64",
@@ -73,6 +74,7 @@ def load() -> C.CDLL:
     lib.b200ref_workspace_min_bytes.argtypes = [i64, i64]
     lib.b200ref_ranks_f64.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, sz, vp]
     lib.b200ref_diagnostics_f64.argtypes = [vp, i64, i64, i64, C.POINTER(dbl), C.c_int, C.POINTER(Outputs), vp, sz, vp]
+    lib.b200ref_diagnostics_ex_f64.argtypes = [vp, i64, i64, i64, C.POINTER(dbl), C.c_int, C.c_int, C.POINTER(Outputs), vp, sz, vp]
     lib.b200ref_stats_f64.argtypes = [vp, i64, i64, C.POINTER(dbl), C.c_int, C.POINTER(Outputs), vp, sz, vp]
     lib.b200ref_compare_f64.argtypes = [vp, vp, i64, dbl, vp, vp, vp, vp]
     lib.b200ref_checks_f64.argtypes = [vp, vp, i64, C.POINTER(C.c_uint8), vp]

@@ -105,12 +105,16 @@ def _alloc_outputs(p: int, nq: int, diag: bool, dev) -> tuple[dict[str, torch.Te
 
 
 def diagnostics_batch(x, quantiles=_DEFAULT_Q, workspace: Workspace | None = None,
-                      ws_cap_bytes: int | None = None) -> dict[str, torch.Tensor]:
+                      ws_cap_bytes: int | None = None, ess_truncation: str = "first_negative") -> dict[str, torch.Tensor]:
     """rhat / ess_bulk / ess_tail (+ mean, std, quantiles, median) for x[P, C, N].
 
     Batched form of ``split_rhat`` / ``ess_bulk`` / ``ess_tail`` (diagnostics.py:13-73).
     No chain-count guard here (the scalar shims in ``diagnostics`` apply it).
+    ``ess_truncation="geyer"`` is an extension (Geyer's initial monotone sequence instead of the
+    reference's first-negative rule, diagnostics.py:172-176); the default is the reference's rule.
     """
+    if ess_truncation not in _native.ESS_MODES:
+        raise ValueError(f"ess_truncation must be one of {sorted(_native.ESS_MODES)}; got {ess_truncation!r}")
     lib = _native.load()
     xt = to_device(x)
     p, c, n = xt.shape
@@ -120,8 +124,9 @@ def diagnostics_batch(x, quantiles=_DEFAULT_Q, workspace: Workspace | None = Non
         return t
     ws = (workspace or _WS).for_shape(p, c, n, cap_bytes=ws_cap_bytes)
     qarr = (C.c_double * max(len(qs), 1))(*qs)
-    _native.check(lib.b200ref_diagnostics_f64(xt.data_ptr(), p, c, n, qarr, len(qs), C.byref(o),
-                                              ws.data_ptr(), ws.numel(), _stream_ptr()))
+    _native.check(lib.b200ref_diagnostics_ex_f64(xt.data_ptr(), p, c, n, qarr, len(qs),
+                                                 _native.ESS_MODES[ess_truncation], C.byref(o),
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr()))
     return t
 
 

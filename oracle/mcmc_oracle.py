@@ -263,6 +263,52 @@ def ess(chains: np.ndarray, return_lag: bool = False):
     return (val, lag) if return_lag else val
 
 
+def ess_geyer(chains: np.ndarray, return_lag: bool = False):
+    """EXTENSION (north-star "Geyer initial-monotone truncation"; the reference truncates at the
+    first negative rho_t, ``diagnostics.py:172-176`` -- parity unpinned, this function IS the definition).
+
+    Same rho_t as ``ess`` (unsplit chains, (n - t)-normalised, same var_hat) with rho_0 := 1.
+    Pairs P_k = rho_{2k} + rho_{2k+1}; the sum stops before the first P_k < 0 (initial positive
+    sequence) and every P_k is capped by its predecessor (initial monotone sequence); only complete
+    pairs (2k + 1 <= n - 1) count.  tau = max(-1 + 2 * sum_k P_k, 1 / log10(m * n)) (the lower bound
+    keeps antithetic chains finite, as in Stan), ESS = m * n / tau.
+    Returned lag = 2k of the first excluded pair (n if the pairs ran out).
+    """
+    m = chains.shape[0]
+    if m == 0:
+        return (math.nan, 0) if return_lag else math.nan
+    n = chains.shape[1]
+    if n < 2:
+        return (math.nan, 0) if return_lag else math.nan
+    means = chains.sum(axis=1) / n
+    mean_total = means.sum() / m
+    var_between = n * ((means - mean_total) ** 2).sum() / (m - 1) if m > 1 else 0.0
+    var_within = _variance_rows(chains).sum() / m
+    var_hat = (n - 1) / n * var_within + var_between / n
+    if var_hat == 0:
+        return (float(m * n), 0) if return_lag else float(m * n)
+    y = chains - means[:, None]
+
+    def rho(t):
+        cov = (y[:, : n - t] * y[:, t:]).sum(axis=1) / (n - t)
+        return cov.sum() / (m * var_hat)
+
+    total, prev, k = 0.0, math.inf, 0
+    stop = n
+    while 2 * k + 1 <= n - 1:
+        pair = (1.0 if k == 0 else rho(2 * k)) + rho(2 * k + 1)
+        if pair < 0:
+            stop = 2 * k
+            break
+        pair = min(pair, prev)
+        total += pair
+        prev = pair
+        k += 1
+    tau = max(-1.0 + 2.0 * total, 1.0 / math.log10(m * n))
+    val = m * n / tau
+    return (val, stop) if return_lag else val
+
+
 def _guard(chains, min_chains: int, what: str):
     """Guards shared by the three public functions (``diagnostics.py:24-30``)."""
     if min_chains < 1:

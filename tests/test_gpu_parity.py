@@ -249,6 +249,30 @@ def test_seeded_against_oracle(B, shape):
     print(f"shape {shape}: mean fraction of tail z bit-equal to the stdlib = {np.mean(fr):.4f}")
 
 
+def test_geyer_truncation_extension(B):
+    """EXTENSION: Geyer initial-monotone ESS (oracle-defined); the default stays the reference's rule."""
+    rng = np.random.default_rng(7)
+    c, n = 4, 6001
+    x = np.stack([_ar1(rng, c, n, 0.0), 3.0 + _ar1(rng, c, n, 0.5), _ar1(rng, c, n, 0.95), -_ar1(rng, c, n, -0.6),
+                  np.round(_ar1(rng, c, n, 0.9), 1)])
+    d = B.diagnostics_batch(x, ess_truncation="geyer")
+    ref = B.diagnostics_batch(x)
+    for i in range(x.shape[0]):
+        _, z = O.rank_normalize(x[i])
+        _, zf = O.rank_normalize(O.fold_chains(x[i]))
+        wb, lb = O.ess_geyer(z, return_lag=True)
+        wt, lt = O.ess_geyer(zf, return_lag=True)
+        assert close(float(d["ess_bulk"][i].item()), wb, TOL), (i, float(d["ess_bulk"][i].item()), wb)
+        assert close(float(d["ess_tail"][i].item()), wt, TOL), (i, float(d["ess_tail"][i].item()), wt)
+        assert int(d["lag_bulk"][i].item()) == lb and int(d["lag_tail"][i].item()) == lt
+        assert close(float(d["rhat"][i].item()), float(ref["rhat"][i].item()), 0.0)  # R-hat is untouched
+        want = O.diagnostics_param(x[i])
+        assert close(float(ref["ess_bulk"][i].item()), want["ess_bulk"], TOL)       # default = reference rule
+    assert int(d["lag_bulk"][2].item()) > 48  # the sticky chain's walk crossed several rounds
+    with pytest.raises(ValueError, match="ess_truncation"):
+        B.diagnostics_batch(x, ess_truncation="fft")
+
+
 def test_long_sticky_chains_many_rounds(B):
     """Chains far longer than any on-chip buffer, and autocorrelation that needs hundreds of lags."""
     rng = np.random.default_rng(99)

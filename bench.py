@@ -310,7 +310,7 @@ def glm_arm(args) -> None:
         logdensity.logistic_lp(X, y, beta, workspace=ws)
     prof = _native.profile_read(reset=True)
     _native.profile(False)
-    k_ms, k_n = prof["k_glm_logistic"]
+    k_ms, k_n = prof["k_glm_lp"]
     flops = 2.0 * n * d * s
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = float(peaks.get("bf16_tflops", 1590.0))
@@ -340,7 +340,7 @@ def glm_arm(args) -> None:
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": s / e2e_s, "unit": "draws/s", "h2d_bytes_per_step": 8 * (n * d + n + s * d),
                 "d2h_bytes_per_step": 8 * s, "steps": 1},
-        "roofline": {"bound": "tensor", "kernel": "k_glm_logistic", "achieved": round(achieved, 1), "peak": peak,
+        "roofline": {"bound": "tensor", "kernel": "k_glm_lp<bernoulli_logit>", "achieved": round(achieved, 1), "peak": peak,
                      "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None,
                      "note": "algorithmic flops 2*N*D*S; the kernel issues 3 bf16 MMAs per product for fp64-class accuracy",
                      "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}},

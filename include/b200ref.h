@@ -206,6 +206,21 @@ int b200ref_gather_rows_f64(const double* in_dev, const int64_t* perm_dev, int64
  * code; parity is pinned against the fp64 oracle only (1e-6 relative).  The contraction runs
  * on the tcgen05 tensor cores with split-bf16 operands and a fused likelihood epilogue. */
 size_t b200ref_glm_workspace_bytes(int64_t N, int64_t D, int64_t S);
+
+/* The same fused contraction + likelihood for the GLM families of the packaged models
+ * (provenance.py:539-640, 704-734; Stan `~` semantics: terms without parameters are dropped):
+ *   B200REF_GLM_BERNOULLI_LOGIT  sum_n y eta - log(1 + exp(eta))
+ *   B200REF_GLM_BINOMIAL_LOGIT   sum_n y eta - trials[n] log(1 + exp(eta))          (trials_dev [N])
+ *   B200REF_GLM_POISSON_LOG      sum_n y eta - exp(eta)
+ *   B200REF_GLM_NORMAL           -N log sigma[s] - sum_n (y - eta)^2 / (2 sigma[s]^2) (sigma_dev [S])
+ * trials_dev / sigma_dev may be null for the families that do not use them. */
+#define B200REF_GLM_BERNOULLI_LOGIT 0
+#define B200REF_GLM_BINOMIAL_LOGIT 1
+#define B200REF_GLM_POISSON_LOG 2
+#define B200REF_GLM_NORMAL 3
+int b200ref_glm_lp_f64(int family, const double* X_dev, const double* y_dev, const double* trials_dev,
+                       const double* beta_dev, const double* sigma_dev, int64_t N, int64_t D, int64_t S,
+                       double* lp_dev, void* ws_dev, size_t ws_bytes, void* stream);
 int b200ref_glm_logistic_lp_f64(const double* X_dev, const double* y_dev, const double* beta_dev,
                                 int64_t N, int64_t D, int64_t S, double* lp_dev,
                                 void* ws_dev, size_t ws_bytes, void* stream);

@@ -53,7 +53,7 @@ enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_F
 const char* const kKernelNames[K_COUNT] = {"k_ztable", "k_sample", "k_bhist", "k_bscan", "k_partition", "k_finish", "k_finish_big",
                                            "k_hist0", "k_radix_pass", "k_rank_codes", "k_param_prep",
                                            "k_merge_partition", "k_fold", "k_moments", "k_decide", "k_finalize",
-                                           "k_summary", "k_compare", "k_checks", "k_synth", "k_glm_prep", "k_glm_logistic", "k_ingest"};
+                                           "k_summary", "k_compare", "k_checks", "k_synth", "k_glm_prep", "k_glm_lp", "k_ingest"};
 struct ProfRec { int id; cudaEvent_t a, b; };
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
@@ -911,7 +911,7 @@ int make_map_bf16(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, ui
 }
 
 struct GlmLayout {
-  size_t bh, bl, xh, xl, yf, part, total;
+  size_t bh, bl, xh, xl, yf, af, part, total;
   int Dpad, n_row_tiles, n_draw_tiles, nsplit;
   void compute(int64_t N, int64_t D, int64_t S) {
     Dpad = (int)((D + GLM_BK - 1) / GLM_BK * GLM_BK);
@@ -924,6 +924,7 @@ struct GlmLayout {
     xh = o; o += up((size_t)N * Dpad * 2);
     xl = o; o += up((size_t)N * Dpad * 2);
     yf = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
+    af = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
     part = o; o += up((size_t)nsplit * S * 8);
     total = o + 1024;
   }
@@ -940,10 +941,14 @@ size_t b200ref_glm_workspace_bytes(int64_t N, int64_t D, int64_t S) {
   return l.total;
 }
 
-int b200ref_glm_logistic_lp_f64(const double* X, const double* y, const double* beta, int64_t N, int64_t D, int64_t S,
-                                double* lp, void* ws, size_t ws_bytes, void* stream) {
+int b200ref_glm_lp_f64(int family, const double* X, const double* y, const double* trials, const double* beta,
+                       const double* sigma, int64_t N, int64_t D, int64_t S, double* lp, void* ws, size_t ws_bytes,
+                       void* stream) {
   g_err[0] = 0;
   if (!X || !y || !beta || !lp || N < 1 || D < 1 || S < 1) return fail(B200REF_ERR_ARG, "bad glm arguments");
+  if (family < GLM_BERNOULLI_LOGIT || family > GLM_NORMAL) return fail(B200REF_ERR_ARG, "unknown glm family %d", family);
+  if (family == GLM_BINOMIAL_LOGIT && !trials) return fail(B200REF_ERR_ARG, "binomial_logit needs the trials vector");
+  if (family == GLM_NORMAL && !sigma) return fail(B200REF_ERR_ARG, "the normal family needs sigma per draw");
   if (D > 65536) return fail(B200REF_ERR_ARG, "D=%lld too large", (long long)D);
   cudaStream_t st = (cudaStream_t)stream;
   GlmLayout L;
@@ -953,11 +958,14 @@ int b200ref_glm_logistic_lp_f64(const double* X, const double* y, const double* 
   __nv_bfloat16 *bh = (__nv_bfloat16*)(w + L.bh), *bl = (__nv_bfloat16*)(w + L.bl);
   __nv_bfloat16 *xh = (__nv_bfloat16*)(w + L.xh), *xl = (__nv_bfloat16*)(w + L.xl);
   float* yf = (float*)(w + L.yf);
+  float* af = (float*)(w + L.af);
   double* part = (double*)(w + L.part);
   const int64_t nb = S * L.Dpad, nx = N * L.Dpad, npad = (int64_t)L.n_row_tiles * GLM_BN;
   LAUNCH(K_GLM_PREP, st, k_glm_split<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(beta, S, (int)D, L.Dpad, bh, bl));
   LAUNCH(K_GLM_PREP, st, k_glm_split<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(X, N, (int)D, L.Dpad, xh, xl));
   LAUNCH(K_GLM_PREP, st, k_glm_y<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(y, N, npad, yf));
+  if (family == GLM_BINOMIAL_LOGIT)
+    LAUNCH(K_GLM_PREP, st, k_glm_y<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(trials, N, npad, af));
   CUDA_TRY(cudaMemsetAsync(part, 0, (size_t)L.nsplit * S * 8, st));
   CUtensorMap mbh, mbl, mxh, mxl;
   int rc;
@@ -968,21 +976,35 @@ int b200ref_glm_logistic_lp_f64(const double* X, const double* y, const double* 
   GlmParams prm;
   prm.N = N; prm.S = S; prm.Dpad = L.Dpad;
   prm.n_row_tiles = L.n_row_tiles; prm.n_draw_tiles = L.n_draw_tiles; prm.nsplit = L.nsplit;
-  prm.yf = yf; prm.lp_part = part;
+  prm.yf = yf; prm.af = af; prm.lp_part = part;
   static bool attr = false;
   if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(k_glm_logistic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_glm_lp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_glm_lp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_glm_lp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_glm_lp<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));
     attr = true;
   }
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(nsm, L.n_draw_tiles * L.nsplit);
-  LAUNCH(K_GLM, st, k_glm_logistic<<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm));
-  LAUNCH(K_GLM_PREP, st, k_glm_reduce<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(part, L.nsplit, S, lp));
+  switch (family) {
+    case GLM_BERNOULLI_LOGIT: LAUNCH(K_GLM, st, k_glm_lp<0><<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm)); break;
+    case GLM_BINOMIAL_LOGIT: LAUNCH(K_GLM, st, k_glm_lp<1><<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm)); break;
+    case GLM_POISSON_LOG: LAUNCH(K_GLM, st, k_glm_lp<2><<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm)); break;
+    default: LAUNCH(K_GLM, st, k_glm_lp<3><<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm)); break;
+  }
+  LAUNCH(K_GLM_PREP, st, k_glm_reduce<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(part, L.nsplit, S,
+                                                                                  family == GLM_NORMAL ? sigma : nullptr, N, lp));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(st));
   return B200REF_OK;
+}
+
+int b200ref_glm_logistic_lp_f64(const double* X, const double* y, const double* beta, int64_t N, int64_t D, int64_t S,
+                                double* lp, void* ws, size_t ws_bytes, void* stream) {
+  return b200ref_glm_lp_f64(GLM_BERNOULLI_LOGIT, X, y, nullptr, beta, nullptr, N, D, S, lp, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

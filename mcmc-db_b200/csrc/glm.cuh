@@ -39,7 +39,14 @@ constexpr int GLM_EPI_THREADS = 256;
 constexpr uint32_t GLM_A_BYTES = GLM_BM * GLM_BK * 2;  // 16 KB
 constexpr uint32_t GLM_B_BYTES = GLM_BN * GLM_BK * 2;  // 32 KB
 constexpr uint32_t GLM_STAGE_BYTES = 2 * GLM_A_BYTES + 2 * GLM_B_BYTES;  // 96 KB
-constexpr size_t GLM_SMEM_BYTES = 1024 + (size_t)GLM_STAGES * GLM_STAGE_BYTES + 2 * GLM_BN * 4 + 256;
+constexpr size_t GLM_SMEM_BYTES = 1024 + (size_t)GLM_STAGES * GLM_STAGE_BYTES + 4 * GLM_BN * 4 + 256;
+
+// Likelihood families (Stan `~` semantics: terms that do not depend on the parameters are dropped):
+//   0 bernoulli_logit  sum_n y eta - softplus(eta)
+//   1 binomial_logit   sum_n y eta - trials softplus(eta)
+//   2 poisson_log      sum_n y eta - exp(eta)
+//   3 normal           sum_n -(y - eta)^2        (the caller scales by 1 / (2 sigma_s^2) and adds -N log sigma_s)
+constexpr int GLM_BERNOULLI_LOGIT = 0, GLM_BINOMIAL_LOGIT = 1, GLM_POISSON_LOG = 2, GLM_NORMAL = 3;
 
 struct GlmParams {
   int64_t N, S;
@@ -48,6 +55,7 @@ struct GlmParams {
   int n_draw_tiles;    // ceil(S / 128)
   int nsplit;          // row-tile slices per draw tile
   const float* yf;     // [n_row_tiles * 256] y as float, padded with 0
+  const float* af;     // [n_row_tiles * 256] binomial trials as float (binomial_logit), else unused
   double* lp_part;     // [nsplit][S], zero-initialised
 };
 
@@ -121,23 +129,31 @@ __global__ void k_glm_y(const double* __restrict__ y, int64_t N, int64_t Npad, f
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Npad) yf[i] = (i < N) ? (float)y[i] : 0.0f;
 }
-__global__ void k_glm_reduce(const double* __restrict__ part, int nsplit, int64_t S, double* __restrict__ lp) {
+// sigma != null (normal family): part holds -SSR_s;  lp = -N log sigma_s + part / (2 sigma_s^2)
+__global__ void k_glm_reduce(const double* __restrict__ part, int nsplit, int64_t S, const double* __restrict__ sigma,
+                             int64_t N, double* __restrict__ lp) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   double a = 0.0;
   for (int h = 0; h < nsplit; ++h) a += part[(size_t)h * S + s];
+  if (sigma) {
+    const double sg = sigma[s];
+    a = -(double)N * log(sg) + 0.5 * a / (sg * sg);
+  }
   lp[s] = a;
 }
 
 // ---- the fused GEMM + likelihood kernel -------------------------------------------------------
+template <int FAM>
 __global__ void __launch_bounds__(GLM_NT, 1)
-k_glm_logistic(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, GlmParams prm) {
   extern __shared__ unsigned char glm_smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)glm_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1 KB
   unsigned char* stage_base = smem;
-  float* ys = (float*)(smem + (size_t)GLM_STAGES * GLM_STAGE_BYTES);  // [2][256]
-  uint64_t* bars = (uint64_t*)(ys + 2 * GLM_BN);
+  float* ys = (float*)(smem + (size_t)GLM_STAGES * GLM_STAGE_BYTES);  // [2][256] y, then [2][256] trials
+  float* as = ys + 2 * GLM_BN;
+  uint64_t* bars = (uint64_t*)(ys + 4 * GLM_BN);
   uint64_t* full = bars;            // [2]  TMA -> MMA
   uint64_t* empty = bars + 2;       // [2]  MMA -> TMA
   uint64_t* tfull = bars + 4;       // [2]  MMA -> epilogue
@@ -236,11 +252,13 @@ k_glm_logistic(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
       for (int rt = t0; rt < t1; ++rt) {
         // stage y for this tile's 256 data rows (one element per epilogue thread)
         ys[abuf * GLM_BN + et] = prm.yf[(size_t)rt * GLM_BN + et];
+        if (FAM == GLM_BINOMIAL_LOGIT) as[abuf * GLM_BN + et] = prm.af[(size_t)rt * GLM_BN + et];
         mbar_wait(&tfull[abuf], aphase);
         tc_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(GLM_EPI_THREADS) : "memory");
         const int64_t nvalid = prm.N - (int64_t)rt * GLM_BN;  // rows of this tile that exist
         const float* yt = ys + abuf * GLM_BN;
+        const float* at = as + abuf * GLM_BN;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int col0 = chalf * 128 + cc * 32;
@@ -250,11 +268,22 @@ k_glm_logistic(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float eta = __uint_as_float(v[j]);
-            const float a = fabsf(eta);
-            float e, l;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * LOG2E));
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-            float term = yt[col0 + j] * eta - (fmaxf(eta, 0.0f) + l * LN2);
+            float term;
+            if (FAM == GLM_BERNOULLI_LOGIT || FAM == GLM_BINOMIAL_LOGIT) {
+              const float a = fabsf(eta);
+              float e, l;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * LOG2E));
+              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+              const float sp = fmaxf(eta, 0.0f) + l * LN2;  // softplus
+              term = yt[col0 + j] * eta - ((FAM == GLM_BINOMIAL_LOGIT) ? at[col0 + j] * sp : sp);
+            } else if (FAM == GLM_POISSON_LOG) {
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(eta * LOG2E));
+              term = yt[col0 + j] * eta - e;
+            } else {
+              const float r = yt[col0 + j] - eta;
+              term = -r * r;
+            }
             if (col0 + j >= nvalid) term = 0.0f;
             part += term;
           }

@@ -16,6 +16,7 @@ ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_NONFINITE = -1, -2, -3, -4
 SUMMARY_K = 20
 MAX_QUANTILES = 8
 ESS_MODES = {"first_negative": 0, "geyer": 1}
+GLM_FAMILIES = {"bernoulli_logit": 0, "binomial_logit": 1, "poisson_log": 2, "normal": 3}
 
 EXPORTS = (
     "b200ref_version", "b200ref_last_error", "b200ref_kernel_launches",
@@ -24,7 +25,7 @@ EXPORTS = (
     "b200ref_ranks_f64", "b200ref_diagnostics_f64", "b200ref_diagnostics_ex_f64", "b200ref_stats_f64",
     "b200ref_compare_f64", "b200ref_checks_f64",
     "b200ref_full_pass_workspace_bytes", "b200ref_full_pass_f64", "b200ref_full_pass_host_f64", "b200ref_synth_fill_f64",
-    "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64",
+    "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64", "b200ref_glm_lp_f64",
     "b200ref_row_order_i64", "b200ref_gather_rows_f64",
 )
 
@@ -86,6 +87,7 @@ def load() -> C.CDLL:
     lib.b200ref_glm_workspace_bytes.restype = sz
     lib.b200ref_glm_workspace_bytes.argtypes = [i64, i64, i64]
     lib.b200ref_glm_logistic_lp_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, sz, vp]
+    lib.b200ref_glm_lp_f64.argtypes = [C.c_int, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, sz, vp]
     lib.b200ref_row_order_i64.argtypes = [vp, vp, i64, C.POINTER(C.c_int), vp]
     lib.b200ref_gather_rows_f64.argtypes = [vp, vp, i64, i64, vp, vp]
     for name in EXPORTS:  # every symbol include/b200ref.h declares must be exported

@@ -29,3 +29,42 @@ def logistic_lp(X, y, beta, workspace: batch.Workspace | None = None) -> torch.T
                                                   lp.data_ptr(), ws.data_ptr(), ws.numel(),
                                                   batch._stream_ptr()))
     return lp
+
+
+def glm_lp(family: str, X, y, beta, trials=None, sigma=None, workspace: batch.Workspace | None = None) -> torch.Tensor:
+    """lp[S] of the likelihood block of a packaged GLM-style model, eta = X @ beta[s] (Stan ``~`` semantics:
+    parameter-free terms dropped):
+
+    * ``"bernoulli_logit"``  ``y ~ bernoulli_logit(X * beta)``          (wells_data-wells_dist.stan:9-11)
+    * ``"binomial_logit"``   ``y ~ binomial_logit(trials, X * beta)``   (provenance.py:567-606)
+    * ``"poisson_log"``      ``y ~ poisson_log(X * beta)``              (provenance.py:609-640)
+    * ``"normal"``           ``y ~ normal(X * beta, sigma)``, ``sigma`` [S] per draw (sblri-blr.stan:12-17)
+    """
+    if family not in _native.GLM_FAMILIES:
+        raise ValueError(f"family must be one of {sorted(_native.GLM_FAMILIES)}; got {family!r}")
+    lib = _native.load()
+    xt, yt, bt = batch.to_device(X), batch.to_device(y).reshape(-1), batch.to_device(beta)
+    n, d = xt.shape
+    s = bt.shape[0]
+    if bt.shape[1] != d or yt.numel() != n:
+        raise ValueError(f"shape mismatch: X {tuple(xt.shape)}, y {tuple(yt.shape)}, beta {tuple(bt.shape)}")
+    tt = st = None
+    if family == "binomial_logit":
+        if trials is None:
+            raise ValueError("binomial_logit needs trials [N]")
+        tt = batch.to_device(trials).reshape(-1)
+        if tt.numel() != n:
+            raise ValueError(f"shape mismatch: trials {tuple(tt.shape)} for N = {n}")
+    if family == "normal":
+        if sigma is None:
+            raise ValueError("the normal family needs sigma [S] (one per draw)")
+        st = batch.to_device(sigma).reshape(-1)
+        if st.numel() != s:
+            raise ValueError(f"shape mismatch: sigma {tuple(st.shape)} for S = {s}")
+    lp = torch.empty(s, dtype=torch.float64, device=xt.device)
+    ws = (workspace or _WS).ensure(int(lib.b200ref_glm_workspace_bytes(n, d, s)))
+    _native.check(lib.b200ref_glm_lp_f64(_native.GLM_FAMILIES[family], xt.data_ptr(), yt.data_ptr(),
+                                         tt.data_ptr() if tt is not None else None, bt.data_ptr(),
+                                         st.data_ptr() if st is not None else None, n, d, s, lp.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), batch._stream_ptr()))
+    return lp

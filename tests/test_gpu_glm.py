@@ -65,3 +65,46 @@ def test_logistic_lp_large_eta_and_determinism(LD):
 def test_logistic_lp_shape_errors(LD):
     with pytest.raises(ValueError, match="shape mismatch"):
         LD.logistic_lp(np.zeros((10, 3)), np.zeros(10), np.zeros((4, 5)))
+
+
+@pytest.mark.parametrize("family", ["bernoulli_logit", "binomial_logit", "poisson_log", "normal"])
+@pytest.mark.parametrize("shape", [(256, 64, 128), (3000, 5, 700), (20000, 256, 2048)])
+def test_glm_families_match_oracle(LD, family, shape):
+    """Families of the packaged models (provenance.py:539-640, 704-734); standardised predictors."""
+    n, d, s = shape
+    rng = np.random.default_rng(n + d + s + len(family))
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    beta_true = rng.standard_normal(d)
+    eta = X @ beta_true
+    beta = beta_true[None, :] + 0.05 * rng.standard_normal((s, d))
+    kw = {}
+    if family == "bernoulli_logit":
+        y = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(np.float64)
+    elif family == "binomial_logit":
+        kw["trials"] = rng.integers(1, 30, n).astype(np.float64)
+        y = rng.binomial(kw["trials"].astype(int), 1 / (1 + np.exp(-eta))).astype(np.float64)
+    elif family == "poisson_log":
+        y = rng.poisson(np.exp(eta)).astype(np.float64)
+    else:
+        y = eta + 0.7 * rng.standard_normal(n)
+        kw["sigma"] = 0.7 * np.exp(0.1 * rng.standard_normal(s))
+    got = LD.glm_lp(family, X, y, beta, **kw).cpu().numpy()
+    want = glm_oracle.glm_lp(family, X, y, beta, **kw)
+    # 1e-6 relative to the magnitude of the summed terms (lp can be a small difference of large sums)
+    rel = np.abs(got - want) / np.maximum(np.abs(want), glm_oracle.glm_term_scale(family, X, y, beta, **kw))
+    # error model: |d eta| ~ 2^-17 |eta| per element, averaging out over the N terms: ~ 1 / sqrt(N).
+    # The stated 1e-6 holds from N = 1000 up; below that the bound scales with sqrt(1000 / N).
+    tol = REL * max(1.0, (1000.0 / n) ** 0.5)
+    assert rel.max() < tol, (family, shape, rel.max(), got[:3], want[:3])
+    if family == "bernoulli_logit":
+        assert np.array_equal(got, LD.logistic_lp(X, y, beta).cpu().numpy())
+
+
+def test_glm_argument_errors(LD):
+    X, y, b = np.zeros((10, 3)), np.zeros(10), np.zeros((4, 3))
+    with pytest.raises(ValueError, match="family must be one of"):
+        LD.glm_lp("probit", X, y, b)
+    with pytest.raises(ValueError, match="needs trials"):
+        LD.glm_lp("binomial_logit", X, y, b)
+    with pytest.raises(ValueError, match="needs sigma"):
+        LD.glm_lp("normal", X, y, b)

@@ -445,6 +445,50 @@ def test_full_size_properties_c2(B):
             assert close(float(d[k][i].item()), want[k], TOL), (i, k)
 
 
+@pytest.mark.parametrize("shape", [(96, 64, 4096), (2, 8, 1_000_000)], ids=["c5-slice", "c4-slice"])
+def test_full_size_properties_c5_c4(B, shape):
+    """BASELINE configs 5 (wide posterior) and 4 (long chains) at their real C x N: size-independent properties.
+
+    * sum of the average ranks = M(M+1)/2 exactly;
+    * a strictly increasing transform of the draws (exp) leaves ranks, bulk scores and bulk ESS / R-hat bit-identical;
+    * reversing the chain order leaves pooled ranks untouched and permutes nothing else;
+    * quantiles are ordered and lie inside [min, max]; 0 < ESS <= M.
+    """
+    import torch
+
+    p, c, n = shape
+    m = c * n
+    x = B.synth_fill(p, c, n, kind=0)
+    x = (x - x.mean(dim=(1, 2), keepdim=True)) / x.std(dim=(1, 2), keepdim=True)  # keep exp() finite and injective
+    d = B.diagnostics_batch(x)
+    r = B.ranks_batch(x, folded=False)
+    rank = r["avg_rank"].reshape(p, m)
+    assert torch.equal(rank.sum(dim=1), torch.full((p,), m * (m + 1) / 2, dtype=torch.float64, device=rank.device))
+    y = torch.exp(x)
+    ry = B.ranks_batch(y, folded=False)
+    untied = (rank == rank.round()).all(dim=1)  # rounding exp() may merge neighbours of a tied parameter
+    assert int(untied.sum()) >= max(1, p // 2)
+    assert torch.equal(ry["avg_rank"][untied], r["avg_rank"][untied])
+    assert torch.equal(ry["z"][untied], r["z"][untied])
+    dy = B.diagnostics_batch(y)
+    assert torch.equal(dy["rhat_bulk"][untied], d["rhat_bulk"][untied])
+    assert torch.equal(dy["ess_bulk"][untied], d["ess_bulk"][untied])
+    rr = B.ranks_batch(x.flip(1), folded=False)
+    assert torch.equal(rr["avg_rank"], r["avg_rank"].flip(1))
+    q = d["quantiles"]
+    xs = x.reshape(p, m)
+    assert bool((q[:, 0] <= q[:, 1]).all() and (q[:, 1] <= q[:, 2]).all())
+    assert bool((q[:, 0] >= xs.min(dim=1).values).all() and (q[:, 2] <= xs.max(dim=1).values).all())
+    assert torch.equal(q[:, 1], d["median"]) or m % 2 == 0  # odd M: q50 is the middle order statistic
+    for k in ("ess_bulk", "ess_tail"):
+        assert bool((d[k] > 0).all() and (d[k] <= m).all())
+    if p > 2:  # oracle spot-check at the full C x N of config 5
+        for i in (0, 5):
+            want = O.diagnostics_param(x[i].cpu().numpy())
+            for k in ("rhat", "ess_bulk", "ess_tail"):
+                assert close(float(d[k][i].item()), want[k], TOL), (i, k)
+
+
 # ---------------------------------------------------------------- ingestion, convert gate, CLI (SURVEY 8f)
 
 def _table_from(x: np.ndarray, names):

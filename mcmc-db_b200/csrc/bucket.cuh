@@ -143,8 +143,15 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     s[j] = k;
   }
   __syncthreads();
+  // bitonic network.  With stride <= 32 the 32 pairs of a warp (in each of its passes over t) stay
+  // inside one 64-element block that only this warp touches, so consecutive such steps need only
+  // a warp barrier; a block barrier separates them from the wider steps.
+  bool prev_local = false;
   for (uint32_t size = 2; size <= S2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      const bool local = stride <= 32;
+      if (local && prev_local) __syncwarp(); else __syncthreads();
+      prev_local = local;
       for (uint32_t t = threadIdx.x; t < S2 / 2; t += 512) {
         const uint32_t i = 2 * t - (t & (stride - 1));
         const uint32_t j = i + stride;
@@ -152,9 +159,9 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
         const uint64_t a = s[i], c = s[j];
         if ((a > c) == up) { s[i] = c; s[j] = a; }
       }
-      __syncthreads();
     }
   }
+  __syncthreads();
   const double lo = key2dbl(s[0]), hi = key2dbl(s[S - 1]);
   const double cs = (hi > lo) ? (double)NCELL / (hi - lo) : 0.0;
   if (threadIdx.x == 0) {
@@ -278,8 +285,9 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
   }
   if (lane == 31) wtot[w] = incl;
   __syncthreads();
-  uint32_t pre = 0;
-  for (int k = 0; k < w; ++k) pre += wtot[k];
+  uint32_t pre = (lane < w) ? wtot[lane] : 0u;  // prefix over the earlier warps (at most 32 of them)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
   const uint32_t excl = pre + incl - run;
   b.boff[(size_t)p * b.bstride + t] = excl;
   if (t == NB1_MAX - 1) b.boff[(size_t)p * b.bstride + NB1_MAX] = excl + run;
@@ -378,8 +386,9 @@ __global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const d
     }
     if (lane == 31) wtot[w] = incl;
     __syncthreads();
-    uint32_t pre = 0;
-    for (int k = 0; k < w; ++k) pre += wtot[k];
+    uint32_t pre = (lane < w) ? wtot[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
     coff[tid] = pre + incl - c;
   }
   __syncthreads();
@@ -439,8 +448,10 @@ __device__ __forceinline__ void fine_scan(FinSmem<CAP, NF>& sm) {
   }
   if (lane == 31) sm.wtot[w] = incl;
   __syncthreads();
-  uint32_t pre = 0;
-  for (int k = 0; k < w; ++k) pre += sm.wtot[k];
+  // exclusive prefix over the warps before this one: lane k < w holds warp k's total, then a warp sum
+  uint32_t pre = (lane < w) ? sm.wtot[lane] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
   uint32_t run = pre + incl - tsum;
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
@@ -492,7 +503,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
                                               uint32_t M, int p, const BucketBufs& b, const FinishOut& fo) {
   const int tid = threadIdx.x;
   // bucket cb = sub-bucket j of coarse bucket c; NF equal-width fine buckets inside it
-  const int nsub = fn->sub, c = cb / nsub;
+  const int nsub = fn->sub, c = (nsub == 1) ? cb : cb / nsub;
   const double jd = (double)(cb - c * nsub);
   const double L = (c == 0) ? fn->lo : fn->sp[c - 1];
   const double fs = fn->fsub[c];
@@ -723,8 +734,9 @@ __global__ void __launch_bounds__(BSW_NT) k_bscan_w(uint32_t M, uint32_t nchunks
   }
   if (lane == 31) wtot[w] = incl;
   __syncthreads();
-  uint32_t pre = 0;
-  for (int k = 0; k < w; ++k) pre += wtot[k];
+  uint32_t pre = (lane < w) ? wtot[lane] : 0u;  // prefix over the earlier warps (at most 32 of them)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
   uint32_t run = pre + incl - tsum;
   uint32_t* boff = b.boff + (size_t)p * b.bstride;
 #pragma unroll

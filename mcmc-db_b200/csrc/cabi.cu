@@ -90,9 +90,16 @@ struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+// one pair of helper streams per (host thread, device): a process may drive several GPUs
 SideStream& side_stream(int slot = 0) {
-  thread_local SideStream pool[2];
-  SideStream& ss = pool[slot & 1];
+  thread_local SideStream pool[MAX_DEVICES][2];
+  SideStream& ss = pool[current_device()][slot & 1];
   if (!ss.s) {
     cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
@@ -322,7 +329,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   double* zodd = (double*)(w + L.zodd);
   int* flag = (int*)(w + L.flag);
   char* wb = w + L.header;
-  static bool part_attr = false;
+  static bool part_attr_dev[MAX_DEVICES] = {};  // function attributes are per device
+  bool& part_attr = part_attr_dev[current_device()];
   if (!part_attr) {
     CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
     CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemSmall)));
@@ -430,13 +438,6 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     LAUNCH(K_FINISH, st, k_finish<<<dim3(nb1 * nsub, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
     LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
     CUDA_TRY(cudaStreamWaitEvent(st, side_stream(slot).join, 0));
-    if (getenv("B200REF_DEBUG")) {
-      int h[2] = {0, 0};
-      cudaMemcpyAsync(&h[0], bb.nbigb, 4, cudaMemcpyDeviceToHost, st);
-      cudaMemcpyAsync(&h[1], bb.nfb, 4, cudaMemcpyDeviceToHost, st);
-      cudaStreamSynchronize(st);
-      fprintf(stderr, "b200ref debug: PB=%d M=%lld nb1=%d sub=%d oversize buckets=%d fallback params=%d\n", PB, (long long)M, nb1, nsub, h[0], h[1]);
-    }
 
     PrepOut po;
     po.quant = (out && out->quantiles) ? out->quantiles + (size_t)p0 * nq : nullptr;
@@ -673,7 +674,8 @@ struct AuxStream {
   cudaEvent_t fork = nullptr, join = nullptr;
 };
 static AuxStream& aux_stream() {
-  thread_local AuxStream ax;
+  thread_local AuxStream pool[MAX_DEVICES];
+  AuxStream& ax = pool[current_device()];
   if (!ax.s) {
     cudaStreamCreateWithFlags(&ax.s, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ax.fork, cudaEventDisableTiming);
@@ -977,7 +979,8 @@ int b200ref_glm_lp_f64(int family, const double* X, const double* y, const doubl
   prm.N = N; prm.S = S; prm.Dpad = L.Dpad;
   prm.n_row_tiles = L.n_row_tiles; prm.n_draw_tiles = L.n_draw_tiles; prm.nsplit = L.nsplit;
   prm.yf = yf; prm.af = af; prm.lp_part = part;
-  static bool attr = false;
+  static bool attr_dev[MAX_DEVICES] = {};
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(k_glm_lp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_glm_lp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GLM_SMEM_BYTES));

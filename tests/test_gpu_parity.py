@@ -489,6 +489,25 @@ def test_full_size_properties_c5_c4(B, shape):
                 assert close(float(d[k][i].item()), want[k], TOL), (i, k)
 
 
+def test_two_devices_from_one_process(B):
+    """Helper streams and kernel attributes are kept per device: one process may drive several GPUs."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(21)
+    x = _workload(rng, 5, 4, 3000)
+    ref = rng.standard_normal((5, 1000))
+    outs = []
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            xd = torch.from_numpy(x).to(f"cuda:{dev}")
+            rd = torch.from_numpy(ref).to(f"cuda:{dev}")
+            summary, _ = B.full_pass(xd, rd, workspace=B.Workspace())
+            outs.append(summary.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1], equal_nan=True) and np.array_equal(outs[0], outs[2], equal_nan=True)
+
+
 # ---------------------------------------------------------------- ingestion, convert gate, CLI (SURVEY 8f)
 
 def _table_from(x: np.ndarray, names):

@@ -117,7 +117,8 @@ struct BucketBufs {
   uint32_t* pidx;      // [PB][M] partitioned positions
   uint64_t* skey;      // [PB][M] sorted keys
   uint32_t* sidx;      // [PB][M] sorted positions
-  uint32_t* kcode;     // [PB][M] k = i + j of each sorted element's tie run
+  uint32_t* kcode;     // [PB][M] k = i + j of each TIED sorted element's run [i, j); such elements carry
+                       //         TIED_BIT in sidx.  An untied element at sorted position t has k = 2t + 1.
   int* sel;            // [PB] (LSD path compatibility: 1 = sorted data are in skey / sidx)
   double* mean;        // [PB]
   double* sd;          // [PB]
@@ -495,22 +496,38 @@ __device__ __forceinline__ void warp_sort_pairs(double* __restrict__ kd, uint32_
   }
 }
 
-// Rank every draw of one coarse bucket (n draws, sorted offset B0) exactly.
+// Fine-bucket function of one bucket: floor(fma(x - L, A, B)) clamped to [0, NF).  Bucket cb is
+// sub-bucket j of coarse bucket c (lower bound L, sub-bucket scale fs): A = fs * NF, B = -j * NF.
+// Monotone in x (one subtraction, one fused multiply-add, A >= 0), which is all exactness needs.
+struct FineFn {
+  double L, A, B;
+};
+
+template <int NF>
+__device__ __forceinline__ FineFn make_fine(const BucketFn* fn, int cb, int nsub) {
+  const int sh = 31 - __clz(nsub);  // nsub is a power of two
+  const int c = cb >> sh;
+  FineFn f;
+  f.L = (c == 0) ? fn->lo : fn->sp[c - 1];
+  f.A = fn->fsub[c] * (double)NF;
+  f.B = -(double)((cb - (c << sh)) * NF);  // 0 when the coarse buckets are the buckets (nsub == 1)
+  return f;
+}
+
+template <int NF>
+__device__ __forceinline__ int fine_bucket(const FineFn& ff, double x) {
+  // cvt.rmi.s32.f64 saturates (NaN -> 0), the integer clamp finishes the job
+  return min(max(__double2int_rd(fma(x - ff.L, ff.A, ff.B)), 0), NF - 1);
+}
+
+// Rank every draw of one bucket (n draws, sorted offset B0) exactly.
 // TWO_PASS = false: the bucket is read once into registers (n <= NT * IPT);
 // TWO_PASS = true : any n <= CAP, the bucket is read twice and slots come from cursors.
 template <int NT, int NF, int CAP, int IPT, bool TWO_PASS>
-__device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const BucketFn* fn, int cb, uint32_t B0, uint32_t n,
+__device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn ff, uint32_t B0, uint32_t n,
                                               uint32_t M, int p, const BucketBufs& b, const FinishOut& fo) {
   const int tid = threadIdx.x;
-  // bucket cb = sub-bucket j of coarse bucket c; NF equal-width fine buckets inside it
-  const int nsub = fn->sub, c = (nsub == 1) ? cb : cb / nsub;
-  const double jd = (double)(cb - c * nsub);
-  const double L = (c == 0) ? fn->lo : fn->sp[c - 1];
-  const double fs = fn->fsub[c];
-  auto fine = [&](double x) -> int {
-    const double t = ((x - L) * fs - jd) * (double)NF;
-    return (t >= 0.0) ? ((t < (double)NF) ? (int)t : NF - 1) : 0;
-  };
+  auto fine = [&](double x) -> int { return fine_bucket<NF>(ff, x); };
   for (int i = tid; i < NF; i += NT) sm.fh[i] = 0;
   if (tid == 0) sm.nbig = 0;
   __syncthreads();
@@ -592,8 +609,8 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
     const uint32_t i = B0 + a + less;
     const uint32_t pos = i + eqb;
     ok[pos] = dbl2key(k);
-    oi[pos] = sm.i2[s];
-    oc[pos] = 2 * i + eq;  // i + j with j = i + eq
+    oi[pos] = (eq > 1u) ? (sm.i2[s] | TIED_BIT) : sm.i2[s];
+    if (eq > 1u) oc[pos] = 2 * i + eq;  // i + j with j = i + eq
     if (orank) orank[sm.i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
   }
   // big fine buckets (heavy ties or a density spike): one warp per bucket
@@ -625,8 +642,8 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const Bucket
       const uint32_t i = B0 + a + less;
       const uint32_t pos = i + eqb;
       ok[pos] = dbl2key(k);
-      oi[pos] = sm.i2[s];
-      oc[pos] = 2 * i + eq;
+      oi[pos] = (eq > 1u) ? (sm.i2[s] | TIED_BIT) : sm.i2[s];
+      if (eq > 1u) oc[pos] = 2 * i + eq;
       if (orank) orank[sm.i2[s]] = (double)(2 * i + eq + 1u) * 0.5;
     }
   }
@@ -824,37 +841,86 @@ __global__ void __launch_bounds__(PART_NT) k_partition_w(const double* __restric
 using FinSmemSmall = FinSmem<CAP1, NFINE>;
 using FinSmemBig = FinSmem<CAPBIG, NFINE_BIG>;
 
-// one CTA per coarse bucket of at most CAP1 draws
+// FIN_BPC consecutive buckets (each at most CAP1 draws) of one parameter per CTA: the bucket offsets
+// and the flags arrive in one round trip, and while a bucket is ranked the next one's keys, positions
+// and bucket function are already on their way (L1 / L2 prefetch: no registers, no staging buffer).
 #ifndef B200REF_FIN_OCC
 #define B200REF_FIN_OCC 6
 #endif
+#ifndef B200REF_FIN_BPC
+#define B200REF_FIN_BPC 4
+#endif
+#ifndef B200REF_FIN_PF
+#define B200REF_FIN_PF 1  // 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2
+#endif
+constexpr int FIN_BPC = B200REF_FIN_BPC;
+
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#if B200REF_FIN_PF == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif B200REF_FIN_PF == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, BucketBufs b, FinishOut fo) {
   extern __shared__ __align__(16) unsigned char fin_smem_raw[];
   FinSmemSmall& sm = *reinterpret_cast<FinSmemSmall*>(fin_smem_raw);
-  const int p = blockIdx.y;
-  if (b.fallback[p]) return;
-  const int cb = blockIdx.x;
+  __shared__ uint32_t sbo[FIN_BPC + 2];
+  const int p = blockIdx.y, tid = threadIdx.x;
+  const int nsub = choose_sub(M), nbt = choose_nb1(M) * nsub;  // what k_sample stored in fn
+  const int cb0 = blockIdx.x * FIN_BPC;
+  if (cb0 >= nbt) return;
   const BucketFn* fn = b.fn + p;
-  if (cb >= fn->nb1 * fn->sub) return;
-  const uint32_t B0 = b.boff[(size_t)p * b.bstride + cb];
-  const uint32_t n = b.boff[(size_t)p * b.bstride + cb + 1] - B0;
-  if (n == 0 || n > (uint32_t)CAP1) return;  // oversize buckets: k_finish_big
-  finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, fn, cb, B0, n, M, p, b, fo);
+  const uint8_t fb = b.fallback[p];
+  if (tid <= FIN_BPC) sbo[tid] = b.boff[(size_t)p * b.bstride + min(cb0 + tid, nbt)];
+  __syncthreads();
+  if (fb) return;
+  const uint32_t* pi0 = b.pidx + (size_t)p * M;
+  const uint64_t* pk0 = b.pkey + (size_t)p * M;
+  const int sh = 31 - __clz(nsub);
+#pragma unroll 1
+  for (int q = 0; q < FIN_BPC; ++q) {
+    const int cb = cb0 + q;
+    if (cb >= nbt) break;
+    const uint32_t B0 = sbo[q], n = sbo[q + 1] - B0;
+    const FineFn ff = make_fine<NFINE>(fn, cb, nsub);
+#if B200REF_FIN_PF != 0
+    if (q + 1 < FIN_BPC && cb + 1 < nbt) {
+      const uint32_t nB0 = sbo[q + 1], nn = min(sbo[q + 2] - nB0, (uint32_t)CAP1);
+      // one prefetch per 128-byte line of the next bucket's keys and positions, and of its bucket function
+      const uintptr_t ka = (uintptr_t)(pk0 + nB0), ke = ka + (size_t)nn * 8;
+      const uintptr_t ia = (uintptr_t)(pi0 + nB0), ie = ia + (size_t)nn * 4;
+      const uint32_t nlk = nn ? (uint32_t)(((ke - 1) >> 7) - (ka >> 7)) + 1u : 0u;
+      const uint32_t nli = nn ? (uint32_t)(((ie - 1) >> 7) - (ia >> 7)) + 1u : 0u;
+      for (uint32_t l = tid; l < nlk + nli; l += FIN_NT)
+        prefetch_line((const void*)(l < nlk ? ((ka >> 7) + l) << 7 : ((ia >> 7) + (l - nlk)) << 7));
+      const int c1 = (cb + 1) >> sh;
+      if (tid == FIN_NT - 1) prefetch_line(&fn->fsub[c1]);
+      if (tid == FIN_NT - 2 && c1 > 0) prefetch_line(&fn->sp[c1 - 1]);
+    }
+#endif
+    if (n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
+      finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, ff, B0, n, M, p, b, fo);
+      __syncthreads();
+    }
+  }
 }
 
-// oversize coarse buckets (CAP1 < n <= CAPBIG: a few heavily repeated values): a small grid
+// oversize buckets (CAP1 < n <= CAPBIG: a few heavily repeated values): a small grid
 // strides over the list k_bscan built
 __global__ void __launch_bounds__(FINB_NT) k_finish_big(uint32_t M, BucketBufs b, FinishOut fo) {
   extern __shared__ __align__(16) unsigned char fin_smem_raw[];
   FinSmemBig& sm = *reinterpret_cast<FinSmemBig*>(fin_smem_raw);
   const int nbig = *b.nbigb;
+  const int nsub = choose_sub(M);
   for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
     const int p = b.biglist[2 * q], cb = b.biglist[2 * q + 1];
     if (b.fallback[p]) continue;
     const uint32_t B0 = b.boff[(size_t)p * b.bstride + cb];
     const uint32_t n = b.boff[(size_t)p * b.bstride + cb + 1] - B0;
     __syncthreads();
-    finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true>(sm, b.fn + p, cb, B0, n, M, p, b, fo);
+    finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true>(sm, make_fine<NFINE_BIG>(b.fn + p, cb, nsub), B0, n, M, p, b, fo);
   }
 }
 

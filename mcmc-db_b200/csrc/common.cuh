@@ -7,6 +7,9 @@
 namespace b200ref {
 
 constexpr unsigned FULL = 0xffffffffu;
+// Bit 31 of a sorted element's original position (C*N < 2^31): the element belongs to a tie run and
+// its code k = i + j is in kcode; an untied element at sorted position t has k = 2t + 1.
+constexpr uint32_t TIED_BIT = 0x80000000u;
 
 // Order-preserving map double -> uint64.  -0.0 is canonicalised to +0.0 first
 // because the reference groups ties with Python `==` (diagnostics.py:116), under

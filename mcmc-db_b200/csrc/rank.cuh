@@ -5,8 +5,8 @@
 //                     point of the folded order, numpy-linear quantiles
 //                     (backends_numpy.py:44) and their order statistics.
 //   k_rank_codes      (LSD fallback path only) one tile of the sorted keys: tie runs
-//                     by equality (diagnostics.py:113-122) -> k = i + j per sorted element.
-//                     The distribution-sort path gets k from k_finish directly.
+//                     by equality (diagnostics.py:113-122) -> k = i + j per sorted element
+//                     (all marked tied).  The distribution-sort path gets k from k_finish directly.
 //   k_merge_partition merge-path split points of the folded order.
 //   k_fold            folded values |v - med| (diagnostics.py:98) are monotone on each
 //                     side of the median, so their ascending order is the MERGE of the
@@ -27,16 +27,16 @@ constexpr int RANK_TILE = RANK_NT * RANK_IPT;
 
 struct RankBufs {
   const uint64_t* key[2];  // sorted keys are in key[sel[p]]
-  const uint32_t* idx[2];
+  uint32_t* idx[2];
   const int* sel;
-  uint32_t* kcode;     // [PB][M] k = i + j per sorted element
+  uint32_t* kcode;     // [PB][M] k = i + j of the TIED sorted elements (flagged by TIED_BIT in idx)
   const uint8_t* fallback;  // [PB] 1 = parameter went through the LSD path
   const int* nfb;           // number of such parameters
   const int* plist;         // [*nfb] their indices
   double* med;         // [PB]
   uint32_t* m0;        // [PB] number of draws strictly below the median
   uint32_t* apos;      // [PB][ntiles+1] merge-path split (count taken from the left part)
-  const double* ztab;  // [2M]
+  const double* ztab;  // [2M]; null when no scores are wanted (stats only)
   const double* zodd;  // [M]  zodd[t] = ztab[2t + 1]
   const int* flag;     // bit0: non-finite input seen -> the ordering is meaningless, kernels return
 };
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(RANK_NT) k_rank_codes(RankBufs b, uint32_t M, 
   const int p = b.plist[q];
   const int s = b.sel[p];
   const uint64_t* keys = b.key[s] + (size_t)p * M;
-  const uint32_t* idx = b.idx[s] + (size_t)p * M;
+  uint32_t* idx = b.idx[s] + (size_t)p * M;
   __syncthreads();
   for (uint32_t e = threadIdx.x; e < n; e += RANK_NT) sv[pidx8(e + 1)] = keys[gbase + e];
   if (threadIdx.x == 0) sv[0] = has_prev ? keys[gbase - 1] : 0;
@@ -169,13 +169,16 @@ __global__ void __launch_bounds__(RANK_NT) k_rank_codes(RankBufs b, uint32_t M, 
 
   uint32_t k[RANK_IPT];
   tie_codes<RANK_NT, RANK_IPT>(sv, n, gbase, has_prev, has_next, ext, scan_sm, k);
+  // every element of a fallback parameter is marked tied: k_fold then reads its code from kcode
   uint32_t* kc = b.kcode + (size_t)p * M;
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
     const uint32_t e = threadIdx.x * RANK_IPT + it;
     if (e < n) {
       kc[gbase + e] = k[it];
-      if (rank_out) rank_out[(size_t)p * M + idx[gbase + e]] = (double)(k[it] + 1u) * 0.5;
+      const uint32_t pos = idx[gbase + e] & ~TIED_BIT;
+      idx[gbase + e] = pos | TIED_BIT;
+      if (rank_out) rank_out[(size_t)p * M + pos] = (double)(k[it] + 1u) * 0.5;
     }
   }
   }
@@ -241,19 +244,35 @@ struct FoldOut {
 // walk the windows ~4 elements apart) off the same shared-memory banks.
 __device__ __forceinline__ uint32_t sdi(uint32_t i) { return i + (i >> 2); }
 
+#ifndef B200REF_FOLD_OCC
+#define B200REF_FOLD_OCC 8
+#endif
+
+// first window slot in [lo, hi) whose folded bits are >= d (STRICT = false) or > d (STRICT = true)
+template <bool STRICT>
+__device__ __forceinline__ uint32_t window_bound(const uint64_t* sd, uint32_t lo, uint32_t hi, uint64_t d) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    const uint64_t v = sd[sdi(mid)];
+    if (STRICT ? (v <= d) : (v < d)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // One CTA = RANK_TILE consecutive outputs of the folded (merged) order.
 //  phase 1  every global read of the tile is issued up front and coalesced: the left / right
-//           windows of the sorted sequence (keys -> folded bits, original positions, bulk tie codes);
-//  phase 2  per-thread merge path + serial merge in shared memory, tie detection (rare path: tie codes);
-//  phase 3  striped over the outputs: two table lookups and ONE 16-byte scatter per draw.
-__global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
-  __shared__ uint64_t sd[RANK_TILE + RANK_TILE / 4 + 2];  // left window then right window (folded bits, index sdi()); later: tie codes
-  __shared__ uint32_t sp[RANK_TILE];      // original positions of the window elements
-  __shared__ double szb[RANK_TILE];       // bulk scores of the window elements
-  __shared__ uint16_t ssrc[RANK_TILE];    // merged output -> window slot
-  __shared__ uint64_t sv[RANK_SV];        // merged folded bits (padded index)
-  __shared__ uint32_t ext[2];
-  __shared__ uint32_t scan_sm[RANK_NT / 32];
+//           windows of the sorted sequence (keys -> folded bits in shared memory; original positions
+//           and bulk scores stay in registers), and the tile of untied folded scores;
+//  phase 2  per-thread merge path + serial merge in shared memory: every window slot learns its
+//           merged position; ties are detected on the fly (continuous draws: almost never);
+//  phase 3  per window slot: the folded score of its merged position and ONE 16-byte scatter per draw.
+//           Tiles with ties get their tie runs by binary searches in the two windows.
+__global__ void __launch_bounds__(RANK_NT, B200REF_FOLD_OCC) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
+  __shared__ uint64_t sd[RANK_TILE + RANK_TILE / 4 + 2];  // left window then right window (folded bits, index sdi())
+  __shared__ double szf[RANK_TILE];       // folded scores of the tile's merged positions (no ties)
+  __shared__ uint16_t dest[RANK_TILE];    // window slot -> merged position inside the tile
+  __shared__ uint64_t edge[2];            // merged values just before / after the tile
+  __shared__ uint32_t ext[2];             // tie-run bounds reaching outside the tile
   const int p = blockIdx.y;
   const uint32_t tile = blockIdx.x;
   if (*b.flag & 1) return;
@@ -268,65 +287,69 @@ __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, ui
   const uint32_t c0 = gbase - a0, c1 = gbase + n - a1;
   const uint32_t nl = a1 - a0, nr = c1 - c0;
   const bool has_prev = gbase > 0, has_next = gbase + n < M;
+  const int tid = threadIdx.x;
 
   // loads are issued in two batches of RANK_IPT / 2 (clamped indices, no branches) so that every
-  // warp has 16 independent requests in flight instead of one dependent chain per element
+  // warp has 12 independent requests in flight instead of one dependent chain per element
+  uint32_t pi[RANK_IPT];
+  double zb[RANK_IPT];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     constexpr int HB = RANK_IPT / 2;
-    uint32_t tt[HB], pi[HB], kcv[HB];
+    uint32_t tt[HB];
     uint64_t kv[HB];
-    double zo[HB];
 #pragma unroll
     for (int j = 0; j < HB; ++j) {
-      const uint32_t e = min((h * HB + j) * RANK_NT + threadIdx.x, n - 1);
+      const uint32_t e = min((h * HB + j) * RANK_NT + tid, n - 1);
       tt[j] = (e < nl) ? (f.m0 - 1 - (a0 + e)) : (f.m0 + c0 + (e - nl));
     }
+    // bulk score of an untied draw at sorted position t: T[2t + 1] = zodd[t] (read along the window);
+    // tied draws (flagged by k_finish) fetch their run's code instead
 #pragma unroll
     for (int j = 0; j < HB; ++j) {
       kv[j] = f.keys[tt[j]];
-      pi[j] = idx[tt[j]];
-      kcv[j] = kc[tt[j]];
+      pi[h * HB + j] = idx[tt[j]];
+      zb[h * HB + j] = b.zodd[tt[j]];
     }
-    // bulk scores: T[k], k = 2t + 1 for an untied draw -> neighbouring table entries
 #pragma unroll
-    for (int j = 0; j < HB; ++j) zo[j] = b.ztab[min(kcv[j], 2u * M - 1u)];
+    for (int j = 0; j < HB; ++j) {
+      if (pi[h * HB + j] & TIED_BIT) {
+        zb[h * HB + j] = b.ztab[kc[tt[j]]];
+        pi[h * HB + j] &= ~TIED_BIT;
+      }
+    }
     // (slots past the end of a short last tile repeat element n - 1: identical values, same address)
 #pragma unroll
     for (int j = 0; j < HB; ++j) {
-      const uint32_t e = min((h * HB + j) * RANK_NT + threadIdx.x, n - 1);
+      const uint32_t e = min((h * HB + j) * RANK_NT + tid, n - 1);
       sd[sdi(e)] = (uint64_t)__double_as_longlong(fabs(__dsub_rn(key2dbl(kv[j]), f.med)));
-      sp[e] = pi[j];
-      szb[e] = zo[j];
     }
   }
   // scores of the tile's outputs if the folded order has no ties here (the usual case)
-  double zfn[RANK_IPT];
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
-    const uint32_t e = it * RANK_NT + threadIdx.x;
-    zfn[it] = (e < n) ? b.zodd[gbase + e] : 0.0;
+    const uint32_t e = it * RANK_NT + tid;
+    if (e < n) szf[e] = b.zodd[gbase + e];
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     // merged element just before the tile: the larger of the two preceding heads
     uint64_t pv = 0;
     if (a0 > 0) pv = f.L(a0 - 1);
     if (c0 > 0) pv = max(pv, f.R(c0 - 1));
-    sv[0] = pv;
+    edge[0] = pv;
   }
-  if (threadIdx.x == 32) {
+  if (tid == 32) {
     uint64_t nv = ~0ull;
     if (a1 < f.nL()) nv = f.L(a1);
     if (c1 < f.nR()) nv = min(nv, f.R(c1));
-    sv[pidx8(n + 1)] = nv;
+    edge[1] = nv;
   }
   __syncthreads();
 
-  // per-thread merge path inside the tile; ties (continuous draws: almost never) are detected on
-  // the fly by comparing each output with its predecessor
+  // per-thread merge path inside the tile; ties are detected by comparing each output with its predecessor
   bool tie = false;
   {
-    const uint32_t od = min((uint32_t)threadIdx.x * RANK_IPT, n);
+    const uint32_t od = min((uint32_t)tid * RANK_IPT, n);
     uint32_t lo = (od > nr) ? od - nr : 0, hi = min(od, nl);
     while (lo < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -338,7 +361,7 @@ __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, ui
     uint64_t prev = 0;
     bool have_prev = has_prev;
     if (od == 0) {
-      prev = sv[0];
+      prev = edge[0];
     } else {
       if (la > 0) prev = sd[sdi(la - 1)];
       if (lc > 0) prev = max(prev, sd[sdi(nl + lc - 1)]);
@@ -353,54 +376,55 @@ __global__ void __launch_bounds__(RANK_NT, 1024 / RANK_NT) k_fold(RankBufs b, ui
         tie |= have_prev && (v == prev);
         prev = v;
         have_prev = true;
-        sv[pidx8(e + 1)] = v;
-        ssrc[e] = (uint16_t)(takeL ? la : nl + lc);
+        dest[takeL ? la : nl + lc] = (uint16_t)e;
         if (takeL) { ++la; vl = (la < nl) ? sd[sdi(la)] : ~0ull; }
         else       { ++lc; vr = (lc < nr) ? sd[sdi(nl + lc)] : ~0ull; }
-        if (e == n - 1) tie |= has_next && (sv[pidx8(n + 1)] == v);
+        if (e == n - 1) tie |= has_next && (edge[1] == v);
       }
     }
   }
   const int any_tie = __syncthreads_or(tie);
-  uint32_t* sk = reinterpret_cast<uint32_t*>(sd);  // sd is dead after the merge: reuse for k codes
   if (any_tie) {
-    if (threadIdx.x == 0) ext[0] = (has_prev && sv[0] == sv[pidx8(1)]) ? f.count_less(sv[pidx8(1)]) : 0;
-    if (threadIdx.x == 32)
-      ext[1] = (has_next && sv[pidx8(n + 1)] == sv[pidx8(n)]) ? f.count_leq(sv[pidx8(n)]) : 0;
-    __syncthreads();
-    uint32_t k[RANK_IPT];
-    tie_codes<RANK_NT, RANK_IPT>(sv, n, gbase, has_prev, has_next, ext, scan_sm, k);
-#pragma unroll
-    for (int it = 0; it < RANK_IPT; ++it) {
-      const uint32_t e = threadIdx.x * RANK_IPT + it;
-      if (e < n) sk[e] = k[it];
+    // smallest / largest folded value of the tile; a run touching them may reach outside the tile
+    if (tid == 0) {
+      const uint64_t v0 = min(nl ? sd[sdi(0)] : ~0ull, nr ? sd[sdi(nl)] : ~0ull);
+      ext[0] = (has_prev && edge[0] == v0) ? f.count_less(v0) : gbase;
+    }
+    if (tid == 32) {
+      const uint64_t v1 = max(nl ? sd[sdi(nl - 1)] : 0ull, nr ? sd[sdi(nl + nr - 1)] : 0ull);
+      ext[1] = (has_next && edge[1] == v1) ? f.count_leq(v1) : gbase + n;
     }
     __syncthreads();
   }
-  // striped output: consecutive lanes -> consecutive merged positions; both table lookups of the
-  // thread's outputs are issued before any is used, then only the 16-byte scatter is random.
+  // per window slot (the order the loads came in): folded score of the slot's merged position, then
+  // the only random access, the 16-byte scatter
   const size_t pbase = (size_t)p * M;
-  uint32_t pos[RANK_IPT], kk[RANK_IPT];
-  double zb[RANK_IPT], zf[RANK_IPT];
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
-    const uint32_t e = it * RANK_NT + threadIdx.x;
-    const uint32_t src = (e < n) ? ssrc[e] : 0;
-    pos[it] = sp[src];
-    zb[it] = szb[src];
-    kk[it] = any_tie ? ((e < n) ? sk[e] : 1u) : 2u * (gbase + min(e, n - 1)) + 1u;
-    zf[it] = any_tie ? b.ztab[kk[it]] : zfn[it];
-  }
-#pragma unroll
-  for (int it = 0; it < RANK_IPT; ++it) {
-    const uint32_t e = it * RANK_NT + threadIdx.x;
-    if (e < n) {
-      if (o.zz) {
-        o.zz[pbase + pos[it]] = make_double2(zb[it], zf[it]);
+    const uint32_t w = it * RANK_NT + tid;
+    if (w < n) {
+      uint32_t kk;
+      double zf;
+      if (!any_tie) {
+        const uint32_t e = dest[w];
+        kk = 2u * (gbase + e) + 1u;
+        zf = szf[e];
       } else {
-        if (o.z) o.z[pbase + pos[it]] = zb[it];
-        if (o.zf) o.zf[pbase + pos[it]] = zf[it];
-        if (o.rankf) o.rankf[pbase + pos[it]] = (double)(kk[it] + 1u) * 0.5;
+        // tie run [i, j) of this slot's folded value in the whole folded order
+        const uint64_t d = sd[sdi(w)];
+        const uint32_t il = window_bound<false>(sd, 0, nl, d) + (window_bound<false>(sd, nl, nl + nr, d) - nl);
+        const uint32_t jl = window_bound<true>(sd, 0, nl, d) + (window_bound<true>(sd, nl, nl + nr, d) - nl);
+        const uint32_t i = (il == 0) ? ext[0] : gbase + il;
+        const uint32_t j = (jl == n) ? ext[1] : gbase + jl;
+        kk = i + j;
+        zf = b.ztab[kk];
+      }
+      if (o.zz) {
+        o.zz[pbase + pi[it]] = make_double2(zb[it], zf);
+      } else {
+        if (o.z) o.z[pbase + pi[it]] = zb[it];
+        if (o.zf) o.zf[pbase + pi[it]] = zf;
+        if (o.rankf) o.rankf[pbase + pi[it]] = (double)(kk + 1u) * 0.5;
       }
     }
   }

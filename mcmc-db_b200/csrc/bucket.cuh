@@ -72,9 +72,8 @@ __host__ __device__ inline int choose_sub(int64_t M) {
 }
 
 __device__ __forceinline__ int cell_of(double x, double lo, double cs) {
-  const double t = (x - lo) * cs;
-  int c = (t >= 0.0) ? ((t < (double)NCELL) ? (int)t : NCELL - 1) : 0;  // NaN (inf * 0) -> 0
-  return c;
+  // cvt.rmi.s32.f64 saturates and maps NaN (inf * 0) to 0; the integer clamp finishes the job
+  return min(max(__double2int_rd((x - lo) * cs), 0), NCELL - 1);
 }
 
 // number of splitters <= x  (monotone in x)
@@ -117,6 +116,8 @@ struct BucketBufs {
   uint32_t* pidx;      // [PB][M] partitioned positions
   uint64_t* skey;      // [PB][M] sorted keys
   uint32_t* sidx;      // [PB][M] sorted positions
+  uint32_t* bmeta;     // [PB][M] narrow path, between k_bhist and k_partition: bucket << 16 | arrival rank of the
+                       //         draw among its chunk's draws of that bucket (shares storage with kcode)
   uint32_t* kcode;     // [PB][M] k = i + j of each TIED sorted element's run [i, j); such elements carry
                        //         TIED_BIT in sidx.  An untied element at sorted position t has k = 2t + 1.
   int* sel;            // [PB] (LSD path compatibility: 1 = sorted data are in skey / sidx)
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(PART_NT) k_bhist(const double* __restrict__ x,
   const double lo = fn->lo, cs = fn->cs, c0 = fn->c0;
   __syncthreads();
   const uint32_t base = chunk * CHUNK_P;
+  uint32_t* meta = b.bmeta + (size_t)p * M;
   double s1 = 0.0, s2 = 0.0;
   bool bad = false;
 #pragma unroll 4
@@ -232,7 +234,10 @@ __global__ void __launch_bounds__(PART_NT) k_bhist(const double* __restrict__ x,
       const double d = v - c0;
       s1 += d;
       s2 = fma(d, d, s2);
-      atomicAdd(&cnt[coarse_of(v, lo, cs, sp, lut)], 1u);
+      // bucket and arrival rank inside this chunk's share of the bucket: k_partition places the draw
+      // from this word alone (no second evaluation of the bucket function, no second counting pass)
+      const uint32_t c = (uint32_t)coarse_of(v, lo, cs, sp, lut);
+      meta[e] = (c << 16) | atomicAdd(&cnt[c], 1u);
     }
   }
   // deterministic block sums (fixed tree)
@@ -315,102 +320,92 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
 
 // ---------------------------------------------------------------- k_partition
 struct PartSmem {
-  uint64_t skey[CHUNK_P];
-  double sp[NB1_MAX];
-  uint32_t cnt[NB1_MAX];
-  uint32_t coff[NB1_MAX];
-  uint32_t goff[NB1_MAX];
+  uint64_t skey[CHUNK_P];   // the chunk's keys in bucket order
+  uint32_t smeta[CHUNK_P];  // bucket << 16 | index inside the chunk
+  uint32_t coff[NB1_MAX];   // start of each bucket inside the chunk
+  uint32_t delta[NB1_MAX];  // (start of this chunk's run in the bucket's global range) - coff
   uint32_t wtot[PART_NT / 32];
-  uint16_t lut[NCELL + 2];
-  uint16_t sloc[CHUNK_P];
-  uint8_t sbk[CHUNK_P];
 };
 
 #ifndef B200REF_PART_OCC
 #define B200REF_PART_OCC 3
 #endif
+constexpr int PART_HB = PART_IPT / 2;  // draws per thread and load batch
+
+// One CTA per 4096-draw chunk: the (bucket, arrival rank) word k_bhist left for every draw gives its slot
+// in the chunk's bucket-ordered staging tile directly; the tile then leaves in runs (coalesced stores).
 __global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
                                                         BucketBufs b) {
   extern __shared__ __align__(16) unsigned char part_smem_raw[];
   PartSmem& sm = *reinterpret_cast<PartSmem*>(part_smem_raw);
-  double* sp = sm.sp;
-  uint16_t* lut = sm.lut;
-  uint32_t* cnt = sm.cnt;
-  uint32_t* coff = sm.coff;
-  uint32_t* goff = sm.goff;
-  uint32_t* wtot = sm.wtot;
-  uint64_t* skey = sm.skey;
-  uint16_t* sloc = sm.sloc;
-  uint8_t* sbk = sm.sbk;
   const int p = blockIdx.y;
   if (b.fallback[p]) return;
   const uint32_t chunk = blockIdx.x;
-  const BucketFn* fn = b.fn + p;
   const double* xp = x + (size_t)p * M;
+  const uint32_t* meta = b.bmeta + (size_t)p * M;
   const int tid = threadIdx.x;
-  for (int i = tid; i < NB1_MAX; i += PART_NT) {
-    sp[i] = fn->sp[i];
-    cnt[i] = 0;
-    goff[i] = b.cnt[((size_t)p * nchunks + chunk) * NB1_MAX + i];
-  }
-  for (int i = tid; i < NCELL + 2; i += PART_NT) lut[i] = fn->lut[i];
-  const double lo = fn->lo, cs = fn->cs;
-  __syncthreads();
   const uint32_t base = chunk * CHUNK_P;
   const uint32_t n = min((uint32_t)CHUNK_P, M - base);
-  double v[PART_IPT];
-  uint32_t r[PART_IPT];
-  uint8_t bk[PART_IPT];
+  // first batch of loads in flight while the offsets are prepared
+  double v[PART_HB];
+  uint32_t m[PART_HB];
 #pragma unroll
-  for (int it = 0; it < PART_IPT; ++it) {
-    const uint32_t e = it * PART_NT + tid;
-    v[it] = (e < n) ? xp[base + e] : 0.0;
+  for (int it = 0; it < PART_HB; ++it) {
+    const uint32_t e = min(it * PART_NT + tid, n - 1);
+    v[it] = xp[base + e];
+    m[it] = meta[base + e];
   }
-#pragma unroll
-  for (int it = 0; it < PART_IPT; ++it) {
-    const uint32_t e = it * PART_NT + tid;
-    if (e < n) {
-      const int c = coarse_of(v[it], lo, cs, sp, lut);
-      bk[it] = (uint8_t)c;
-      r[it] = atomicAdd(&cnt[c], 1u);
-    }
-  }
-  __syncthreads();
-  {  // exclusive scan of cnt[256] with 256 threads
+  {  // this chunk's count per bucket = next chunk's offset - this chunk's offset; exclusive scan -> coff
+    const uint32_t* g = b.cnt + ((size_t)p * nchunks + chunk) * NB1_MAX;
+    const uint32_t g0 = g[tid];
+    const uint32_t g1 = (chunk + 1 < nchunks) ? g[NB1_MAX + tid] : b.boff[(size_t)p * b.bstride + tid + 1];
     const int lane = tid & 31, w = tid >> 5;
-    const uint32_t c = cnt[tid];
+    const uint32_t c = g1 - g0;
     uint32_t incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t nn = __shfl_up_sync(FULL, incl, o);
       if (lane >= o) incl += nn;
     }
-    if (lane == 31) wtot[w] = incl;
+    if (lane == 31) sm.wtot[w] = incl;
     __syncthreads();
-    uint32_t pre = (lane < w) ? wtot[lane] : 0u;
+    uint32_t pre = (lane < w) ? sm.wtot[lane] : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
-    coff[tid] = pre + incl - c;
+    const uint32_t co = pre + incl - c;
+    sm.coff[tid] = co;
+    sm.delta[tid] = g0 - co;
   }
   __syncthreads();
 #pragma unroll
-  for (int it = 0; it < PART_IPT; ++it) {
-    const uint32_t e = it * PART_NT + tid;
-    if (e < n) {
-      const uint32_t slot = coff[bk[it]] + r[it];
-      skey[slot] = dbl2key(v[it]);
-      sloc[slot] = (uint16_t)e;
-      sbk[slot] = bk[it];
+  for (int h = 0; h < 2; ++h) {
+    if (h == 1) {
+#pragma unroll
+      for (int it = 0; it < PART_HB; ++it) {
+        const uint32_t e = min((PART_HB + it) * PART_NT + tid, n - 1);
+        v[it] = xp[base + e];
+        m[it] = meta[base + e];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < PART_HB; ++it) {
+      const uint32_t e = (h * PART_HB + it) * PART_NT + tid;
+      if (e < n) {
+        const uint32_t slot = sm.coff[m[it] >> 16] + (m[it] & 0xffffu);
+        sm.skey[slot] = dbl2key(v[it]);
+        sm.smeta[slot] = (m[it] & 0xffff0000u) | e;
+      }
     }
   }
   __syncthreads();
   uint64_t* ok = b.pkey + (size_t)p * M;
   uint32_t* oi = b.pidx + (size_t)p * M;
+#pragma unroll 4
   for (uint32_t s = tid; s < n; s += PART_NT) {
-    const int c = sbk[s];
-    const uint32_t pos = goff[c] + (s - coff[c]);
-    ok[pos] = skey[s];
-    oi[pos] = base + sloc[s];
+    const uint32_t mm = sm.smeta[s];
+    const uint32_t pos = sm.delta[mm >> 16] + s;
+    ok[pos] = sm.skey[s];
+    oi[pos] = base + (mm & 0xffffu);
   }
 }
 
@@ -848,7 +843,7 @@ using FinSmemBig = FinSmem<CAPBIG, NFINE_BIG>;
 #define B200REF_FIN_OCC 6
 #endif
 #ifndef B200REF_FIN_BPC
-#define B200REF_FIN_BPC 4
+#define B200REF_FIN_BPC 8
 #endif
 #ifndef B200REF_FIN_PF
 #define B200REF_FIN_PF 1  // 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2

@@ -371,6 +371,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     bb.skey = (uint64_t*)(wb + L.skey);
     bb.sidx = (uint32_t*)(wb + L.sidx);
     bb.kcode = (uint32_t*)(wb + L.kcode);
+    bb.bmeta = bb.kcode;  // dead before k_finish / k_rank_codes write the tie codes
     bb.sel = (int*)(wb + L.sel);
     bb.mean = (double*)(wb + L.mean);
     bb.sd = (double*)(wb + L.sd);

@@ -417,7 +417,7 @@ struct FinishOut {
 // Shared-memory layout of one finishing CTA (dynamic).
 template <int CAP, int NF>
 struct FinSmem {
-  double kd[CAP];          // canonical values in fine-bucket order
+  double kd[CAP + 4];      // canonical values in fine-bucket order, then 4 x +inf
   uint32_t i2[CAP];        // their original positions
   uint32_t fh[NF];         // fine histogram, then running cursors (two-pass mode)
   uint32_t foff[NF + 1];   // exclusive offsets
@@ -571,6 +571,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
       sm.i2[slot] = pi[e];
     }
   }
+  if (tid < 4) sm.kd[n + tid] = __longlong_as_double(0x7ff0000000000000ll);
   __syncthreads();
   uint64_t* ok = b.skey + (size_t)p * M;
   uint32_t* oi = b.sidx + (size_t)p * M;
@@ -582,25 +583,24 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
     const int fb = fine(k);
     const uint32_t a = sm.foff[fb], e = sm.foff[fb + 1];
     if (e - a > (uint32_t)BIG_FINE) continue;
-    uint32_t less = 0, eq = 0, eqb = 0;
-    // first 4 slots branch-free (covers almost every fine bucket), the rest in a loop
+    // The 4 slots from the bucket's start are read unconditionally: whatever lies past its end belongs
+    // to later fine buckets (strictly larger values) or is the +inf padding, and counts for nothing.
+    uint32_t less = 0, le = 0;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-      const uint32_t t = a + d;
-      const bool in = t < e;
-      const double kt = sm.kd[in ? t : s];
-      less += (in && kt < k);
-      const bool same = in && (kt == k);
-      eq += same;
-      eqb += (same && t < s);
+      const double kt = sm.kd[a + d];
+      less += (kt < k);
+      le += (kt <= k);
     }
     for (uint32_t t = a + 4; t < e; ++t) {
       const double kt = sm.kd[t];
       less += (kt < k);
-      const bool same = (kt == k);
-      eq += same;
-      eqb += (same && t < s);
+      le += (kt <= k);
     }
+    const uint32_t eq = le - less;
+    uint32_t eqb = 0;  // equal values in earlier slots: only tied draws need it
+    if (eq > 1u)
+      for (uint32_t t = a; t < s; ++t) eqb += (sm.kd[t] == k);
     const uint32_t i = B0 + a + less;
     const uint32_t pos = i + eqb;
     ok[pos] = dbl2key(k);

@@ -240,9 +240,14 @@ struct FoldOut {
   double* rankf;
 };
 
-// Index into the folded-bits window: one pad word per 4 keeps the merge's reads (neighbouring threads
-// walk the windows ~4 elements apart) off the same shared-memory banks.
-__device__ __forceinline__ uint32_t sdi(uint32_t i) { return i + (i >> 2); }
+// Index into the folded-bits window: one pad word per 16 keeps the merge's reads (neighbouring threads
+// walk the windows ~4 elements apart) off the same shared-memory banks, and a half-warp's 16 consecutive
+// slots of the striped stores stay contiguous.
+#ifndef B200REF_FOLD_PAD_SH
+#define B200REF_FOLD_PAD_SH 4
+#endif
+constexpr int FOLD_PAD_SH = B200REF_FOLD_PAD_SH;
+__device__ __forceinline__ uint32_t sdi(uint32_t i) { return i + (i >> FOLD_PAD_SH); }
 
 #ifndef B200REF_FOLD_OCC
 #define B200REF_FOLD_OCC 8
@@ -268,7 +273,7 @@ __device__ __forceinline__ uint32_t window_bound(const uint64_t* sd, uint32_t lo
 //  phase 3  per window slot: the folded score of its merged position and ONE 16-byte scatter per draw.
 //           Tiles with ties get their tie runs by binary searches in the two windows.
 __global__ void __launch_bounds__(RANK_NT, B200REF_FOLD_OCC) k_fold(RankBufs b, uint32_t M, uint32_t ntiles, FoldOut o) {
-  __shared__ uint64_t sd[RANK_TILE + RANK_TILE / 4 + 2];  // left window then right window (folded bits, index sdi())
+  __shared__ uint64_t sd[RANK_TILE + (RANK_TILE >> FOLD_PAD_SH) + 2];  // left window then right window (folded bits, index sdi())
   __shared__ double szf[RANK_TILE];       // folded scores of the tile's merged positions (no ties)
   __shared__ uint16_t dest[RANK_TILE];    // window slot -> merged position inside the tile
   __shared__ uint64_t edge[2];            // merged values just before / after the tile

@@ -268,7 +268,7 @@ def gpu_arm(args) -> None:
             "pass_roofline": pass_roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "e2e_bits_equal_device_path": same_bits,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -361,7 +361,7 @@ def glm_arm(args) -> None:
                          "sample": f"{ns} of {s} draws, numpy fp64 oracle (BLAS threads), {cpu_s:.1f} s"},
         "parity": {"draws_checked": int(ns), "max_rel_err": max_rel, "ok": bool(max_rel < 1e-6)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def reference_arm(args) -> None:
@@ -398,10 +398,33 @@ def reference_arm(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def guard_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner when NCCL_DEBUG is set), so the real stdout is kept aside for the result line and file
+    descriptor 1 is pointed at stderr for everything else (this process and its children)."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main() -> None:
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -414,7 +437,7 @@ def main() -> None:
     ap.add_argument("--glm-cpu-draws", type=int, default=512)
     ap.add_argument("--ws-gb", type=float, default=16.0, help="cap of the device workspace")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-params-per-core", type=int, default=24)
+    ap.add_argument("--cpu-params-per-core", type=int, default=64)
     ap.add_argument("--ref-params-per-core", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

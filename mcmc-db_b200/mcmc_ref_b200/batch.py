@@ -30,7 +30,10 @@ def to_device(x) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         t = x.to(device=dev, dtype=torch.float64)
     else:
-        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
+        arr = np.asarray(x, dtype=np.float64)
+        if not (arr.flags.c_contiguous and arr.flags.writeable):  # e.g. a read-only Arrow buffer view
+            arr = np.array(arr, dtype=np.float64, order="C")
+        t = torch.from_numpy(arr).to(dev)
     return t.contiguous()
 
 

@@ -117,6 +117,35 @@ def compare_cmd(model: str, actual_path: Path, tolerance: float, format_: str) -
     raise SystemExit(0 if result.passed else 2)
 
 
+@main.command("log-density")
+@click.argument("model")
+@click.option("--draws", "draws_path", type=click.Path(path_type=Path), default=None,
+              help="CSV of candidate draws (columns named like the packaged draws); default: the packaged reference draws")
+@click.option("--format", "format_", type=click.Choice(["summary", "csv", "json"], case_sensitive=False), default="summary")
+def log_density_cmd(model: str, draws_path: Path | None, format_: str) -> None:
+    """EXTENSION (the reference has no such command): likelihood-block log-density of a packaged GLM-style
+    model over draws, evaluated on the tensor cores (models.packaged_lp)."""
+    draws = _read_actual_csv(draws_path) if draws_path is not None else None
+    lp = reference.log_density(model, draws=draws).cpu().numpy()
+    if format_ == "csv":
+        click.echo("lp")
+        for v in lp:
+            click.echo(repr(float(v)))
+    elif format_ == "json":
+        click.echo(json.dumps([float(v) for v in lp]))
+    else:
+        click.echo(f"draws {lp.size} mean {lp.mean():.6g} sd {lp.std():.6g} min {lp.min():.6g} max {lp.max():.6g}")
+
+
+@main.command("models")
+def models_cmd() -> None:
+    """Packaged models the log-density registry restates (family and Stan source lines)."""
+    from .models import MODELS
+
+    for name in sorted(MODELS):
+        click.echo(f"{name}\t{MODELS[name].family}\t{MODELS[name].source}")
+
+
 @main.command("convert")
 @click.argument("input_path", type=click.Path(path_type=Path))
 @click.option("--name", required=True)

@@ -17,6 +17,24 @@ from .convert import _compute_diagnostics
 from .store import PackagedStore
 
 
+def stan_data(model: str, store=None) -> dict:
+    """reference.py:20-22"""
+    return (store or PackagedStore()).read_stan_data(model)
+
+
+def model_code(model: str, store=None) -> str:
+    """reference.py:25-27"""
+    return (store or PackagedStore()).read_stan_code(model)
+
+
+def log_density(model: str, draws: Mapping[str, Sequence[float]] | None = None, store=None):
+    """EXTENSION (no reference counterpart): likelihood-block log-density of a packaged GLM-style model
+    over draws, on the tensor cores -- see ``models.packaged_lp``."""
+    from .models import packaged_lp
+
+    return packaged_lp(model, draws=draws, store=store)
+
+
 def stats(
     model: str,
     params: Sequence[str] | None = None,

@@ -4,7 +4,7 @@ Resolution order as in the reference: packaged root (``mcmc_ref_data`` / ``mcmc_
 package data if installed, or an explicit ``packaged_root``) first, then the local
 root (``MCMC_REF_LOCAL_ROOT`` or ``~/.mcmc-ref``).  Only what the compare /
 diagnostics path needs: ``open_draws`` with column projection and chain filter,
-``read_meta``, ``list_models``.
+``read_meta``, ``list_models``, and ``read_stan_data`` / ``read_stan_code`` for the log-density extension.
 """
 
 from __future__ import annotations
@@ -63,6 +63,21 @@ class PackagedStore:
         if path is None:
             raise FileNotFoundError(f"metadata not found for model: {model}")
         return json.loads(path.read_text())
+
+    def read_stan_data(self, model: str) -> dict:
+        """``stan_data/<model>.data.json`` (store.py:57-66)."""
+        path = self._resolve(model, "stan_data", ".data.json")
+        if path is None:
+            raise FileNotFoundError(f"stan data not found for model: {model}")
+        return json.loads(path.read_text())
+
+    def read_stan_code(self, model: str) -> str:
+        """``stan_code/<model>.stan``, else ``stan_models/<model>.stan`` (store.py:68-77, :110-119)."""
+        for sub in ("stan_code", "stan_models"):
+            path = self._resolve(model, sub, ".stan")
+            if path is not None:
+                return path.read_text()
+        raise FileNotFoundError(f"stan code not found for model: {model}")
 
     def open_draws(self, model: str, params: Sequence[str] | None = None, chains: Sequence[int] | None = None,
                    batch_size: int = 1024):

@@ -31,8 +31,8 @@ class GlmModel:
     family: str                    # a key of _native.GLM_FAMILIES
     response: str                  # expression over stan_data
     columns: tuple[str, ...]       # design-matrix columns: expressions over stan_data; "@M" = every column of matrix M
-    coef: tuple[str, ...]          # draw columns, one per design column; "v[*]" = v[1] .. v[k] for an "@M" block
-    sigma: str | None = None       # draw column (normal family)
+    coef: tuple[str, ...]          # draw columns, one per design column; "v[*]" / "v[*,2]" = index 1 .. k over an "@M" block
+    sigma: str | None = None       # draw column (normal family); "=1" = the constant 1 (scale folded into the design)
     trials: str | None = None      # expression over stan_data (binomial_logit)
     source: str = ""               # Stan file (under stan_models/) and the lines restated
 
@@ -114,6 +114,23 @@ MODELS: dict[str, GlmModel] = {
     "radon_pooled_informed": _lin("log_radon_std", "floor_measure_std", coef=("alpha", "beta"), sigma="sigma_y",
                                   source="radon_pooled_informed.stan:15-23"),
     "kilpisjarvi_mod-kilpisjarvi": _lin("y", "x", coef=("alpha", "beta"), source="kilpisjarvi_mod-kilpisjarvi.stan:17-21"),
+    # ---- hierarchical non-centred models: the packaged draws carry the transformed parameters (alpha[j],
+    # theta[j], ...), so the likelihood block is a GLM over one-hot group designs ----
+    "eight_schools-eight_schools_noncentered": GlmModel("normal", "y / sigma", ("@diag(1 / sigma)",), ("theta[*]",), sigma="=1",
+                                                        source="eight_schools-eight_schools_noncentered.stan:11-21"),
+    "eight_schools-noncentered": GlmModel("normal", "y / sigma", ("@diag(1 / sigma)",), ("theta[*]",), sigma="=1",
+                                          source="eight_schools-noncentered.stan:12-20"),
+    "hierarchical_lr-noncentered": GlmModel("normal", "y", ("@onehot(group, J)", "x"), ("alpha[*]", "beta"), sigma="sigma",
+                                            source="hierarchical_lr-noncentered.stan:16-28"),
+    "radon_mn-radon_hierarchical_intercept_noncentered": GlmModel(
+        "normal", "log_radon", ("@onehot(county_idx, J)", "log_uppm", "floor_measure"), ("alpha[*]", "beta[1]", "beta[2]"),
+        sigma="sigma_y", source="radon_mn-radon_hierarchical_intercept_noncentered.stan:16-36"),
+    "varying_slopes-noncentered": GlmModel("normal", "y", ("@onehot(group, J)", "@onehot(group, J) * x[:, None]"),
+                                           ("beta_group[*,1]", "beta_group[*,2]"), sigma="sigma",
+                                           source="varying_slopes-noncentered.stan:15-30"),
+    "bangladesh_contraceptive-noncentered": GlmModel("bernoulli_logit", "use",
+                                                     ("@onehot(district, D)", "@onehot(district, D) * urban[:, None]"),
+                                                     ("a[*]", "b[*]"), source="bangladesh_contraceptive-noncentered.stan:17-31"),
     # ---- non-Gaussian GLMs ----
     "wells_data-wells_dist": GlmModel("bernoulli_logit", "switched", ("1", "dist"), _beta(2),
                                       source="wells_data-wells_dist.stan:9-11"),
@@ -136,6 +153,8 @@ def _env(data: Mapping[str, object]) -> dict[str, object]:
         "mean": lambda v: float(np.mean(v)),
         "sd": lambda v: float(np.std(v, ddof=1)),          # Stan's sd() is the sample standard deviation
         "center": lambda m: m - np.mean(m, axis=0),        # brms' Xc
+        "diag": np.diag,
+        "onehot": lambda idx, k: (np.asarray(idx, dtype=np.int64)[:, None] == np.arange(1, int(k) + 1)[None, :]).astype(np.float64),
     }
     for key, value in data.items():
         env[key] = np.asarray(value, dtype=np.float64) if isinstance(value, (list, tuple)) else value
@@ -168,30 +187,32 @@ def design(model: str, data: Mapping[str, object]) -> tuple[np.ndarray, np.ndarr
     return np.ascontiguousarray(np.concatenate(blocks, axis=1)), y, trials, widths
 
 
+def _expand(name: str, width: int) -> list[str]:
+    return [name.replace("*", str(i)) for i in range(1, width + 1)] if "*" in name else [name]
+
+
 def coefficients(model: str, draws: Mapping[str, Sequence[float]], widths: Sequence[int]) -> tuple[np.ndarray, np.ndarray | None]:
     """(beta [S, D], sigma [S] or None) from a mapping draw column -> values (all chains pooled)."""
     spec = MODELS[model]
-    cols = []
-    for name, width in zip(spec.coef, widths):
-        if name.endswith("[*]"):
-            cols.extend(f"{name[:-3]}[{i}]" for i in range(1, width + 1))
-        else:
-            cols.append(name)
-    missing = [c for c in cols + ([spec.sigma] if spec.sigma else []) if c not in draws]
+    cols = [c for name, width in zip(spec.coef, widths) for c in _expand(name, width)]
+    const_sigma = spec.sigma is not None and spec.sigma.startswith("=")
+    missing = [c for c in cols + ([spec.sigma] if spec.sigma and not const_sigma else []) if c not in draws]
     if missing:
         raise KeyError(f"draws for {model} lack column(s): {', '.join(missing)}")
     beta = np.stack([np.asarray(draws[c], dtype=np.float64) for c in cols], axis=1)
-    sigma = np.asarray(draws[spec.sigma], dtype=np.float64) if spec.sigma else None
+    sigma = None
+    if const_sigma:
+        sigma = np.full(beta.shape[0], float(spec.sigma[1:]))
+    elif spec.sigma:
+        sigma = np.asarray(draws[spec.sigma], dtype=np.float64)
     return np.ascontiguousarray(beta), sigma
 
 
 def draw_columns(model: str, widths: Sequence[int]) -> list[str]:
     """The draw columns ``coefficients`` reads (column projection for ``store.open_draws``)."""
     spec = MODELS[model]
-    cols = []
-    for name, width in zip(spec.coef, widths):
-        cols.extend([f"{name[:-3]}[{i}]" for i in range(1, width + 1)] if name.endswith("[*]") else [name])
-    if spec.sigma:
+    cols = [c for name, width in zip(spec.coef, widths) for c in _expand(name, width)]
+    if spec.sigma and not spec.sigma.startswith("="):
         cols.append(spec.sigma)
     return cols
 

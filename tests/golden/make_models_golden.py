@@ -25,7 +25,8 @@ DATA = Path("/root/reference/packages/mcmc-ref-data/src/mcmc_ref_data/data")
 SUBSET = ["kidiq-kidscore_interaction", "kidiq_with_mom_work-kidscore_mom_work", "kidiq_with_mom_work-kidscore_interaction_z",
           "earnings-logearn_interaction_z", "mesquite-logmesquite_logvas", "nes2000-nes", "sblri-blr",
           "kilpisjarvi_mod-kilpisjarvi", "wells_data-wells_dist", "GLM_Poisson_Data-GLM_Poisson_model",
-          "GLM_Binomial_data-GLM_Binomial_model"]
+          "GLM_Binomial_data-GLM_Binomial_model", "eight_schools-eight_schools_noncentered", "varying_slopes-noncentered",
+          "bangladesh_contraceptive-noncentered"]
 NDRAWS = 96
 
 
@@ -65,10 +66,12 @@ def main():
             # the checkout lacks this model's parquet (.MISSING_LARGE_BLOBS): draws around a crude fit
             if spec.family == "poisson_log":
                 b0 = np.linalg.lstsq(X, np.log(y + 0.5), rcond=None)[0]
+            elif spec.family == "bernoulli_logit":
+                b0 = np.linalg.lstsq(X, 4.0 * (y - 0.5), rcond=None)[0]
             else:
                 p = (y + 0.5) / (trials + 1.0)
                 b0 = np.linalg.lstsq(X, np.log(p / (1 - p)), rcond=None)[0]
-            bs = b0[None, :] * (1.0 + 0.01 * rng.standard_normal((NDRAWS, len(b0))))
+            bs = b0[None, :] + 0.01 * (1.0 + np.abs(b0[None, :])) * rng.standard_normal((NDRAWS, len(b0)))
             draws = {c: bs[:, i].tolist() for i, c in enumerate(cols)}
             origin = "synthetic draws around a least-squares fit (no packaged parquet in this checkout)"
         beta, sigma = models.coefficients(m, draws, widths)
@@ -77,7 +80,7 @@ def main():
         he = hand_eta(m, data, draws)
         if he is not None:
             assert np.allclose(he, X @ beta.T, rtol=1e-13, atol=1e-12), m
-            sg = np.asarray(draws["sigma"])
+            sg = np.asarray(draws["sigma"])  # the three hand-checked models are normal-family
             lp_hand = -len(y) * np.log(sg) - ((y[:, None] - he) ** 2).sum(axis=0) / (2 * sg * sg)
             assert np.allclose(lp_hand, lp, rtol=1e-12), m
         keys = sorted({k for k in data if isinstance(data[k], (list, int, float))})

@@ -43,6 +43,7 @@ def test_registry_shape(M):
         assert spec.family in _native.GLM_FAMILIES, name
         assert spec.source.startswith(name + ".stan:"), name
         assert (spec.sigma is not None) == (spec.family == "normal"), name
+        assert spec.source.split(":")[1].replace("-", "").isdigit(), name
         assert (spec.trials is not None) == (spec.family == "binomial_logit"), name
 
 
@@ -58,9 +59,10 @@ def test_design_and_conditioning_match_oracle(M, model):
     np.testing.assert_allclose(got, want, rtol=1e-13)
     # the conditioning is an exact reparametrisation: same log-density from (X', y', beta')
     Xc, yc, bc = M.condition(spec.family, X, y, beta)
-    assert np.all(Xc[:, 0] == 1.0) and np.abs(Xc[:, 1:].mean(axis=0)).max() < 1e-12
+    assert np.all(Xc[:, 0] == 1.0) and np.abs(Xc).max() <= np.sqrt(len(y)) + 1e-9  # orthonormal columns x sqrt(N)
     again = glm_oracle.glm_lp(spec.family, Xc, yc, bc, trials=trials, sigma=sigma)
-    np.testing.assert_allclose(again, want, rtol=1e-10)
+    # (noise-free pair data: sigma ~ 1e-4 amplifies fp64 rounding of the residuals by 1 / sigma^2)
+    assert (np.abs(again - want) / np.maximum(np.abs(want), np.asarray(g["term_scale"]))).max() < 1e-9
 
 
 def test_missing_draw_column_is_reported(M):
@@ -90,7 +92,12 @@ def test_every_registered_model_fits_its_packaged_draws(M):
         draws = {c: t.column(c).to_numpy() for c in t.column_names if c not in {"chain", "draw"}}
         beta, sigma = M.coefficients(model, draws, widths)
         eta = X @ beta.mean(axis=0)
-        if spec.family == "normal":
+        if spec.family == "normal" and spec.sigma.startswith("="):
+            pass  # eight schools: 8 observations with known scales, nothing to estimate the spread from
+        elif spec.family == "normal" and sigma.mean() < 1e-2 * np.std(y):
+            # noise-free synthetic data (the pair recipes, provenance.py:1174-1343): the fit must be exact
+            assert np.std(y - eta) < 1e-2 * np.std(y), (model, np.std(y - eta))
+        elif spec.family == "normal":
             ratio = np.std(y - eta) / sigma.mean()
             if model in M.PACKAGED_DATA_MISMATCH:
                 assert not 0.8 < ratio < 1.25, (model, ratio)  # documented inconsistency of the packaged data
@@ -99,7 +106,7 @@ def test_every_registered_model_fits_its_packaged_draws(M):
         elif spec.family == "bernoulli_logit":
             assert abs((1 / (1 + np.exp(-eta))).mean() - y.mean()) < 0.01, model
         checked += 1
-    assert checked >= 34
+    assert checked >= 38
 
 
 @pytest.fixture(scope="module")

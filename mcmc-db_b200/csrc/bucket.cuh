@@ -858,12 +858,13 @@ __device__ __forceinline__ void prefetch_line(const void* p) {
 #endif
 }
 
-__global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, BucketBufs b, FinishOut fo) {
+// nsub / nbt: sub-buckets per coarse bucket and buckets per parameter (choose_sub(M), choose_nb1(M) * nsub:
+// what k_sample stored in fn), computed once on the host.
+__global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, int nsub, int nbt, BucketBufs b, FinishOut fo) {
   extern __shared__ __align__(16) unsigned char fin_smem_raw[];
   FinSmemSmall& sm = *reinterpret_cast<FinSmemSmall*>(fin_smem_raw);
   __shared__ uint32_t sbo[FIN_BPC + 2];
   const int p = blockIdx.y, tid = threadIdx.x;
-  const int nsub = choose_sub(M), nbt = choose_nb1(M) * nsub;  // what k_sample stored in fn
   const int cb0 = blockIdx.x * FIN_BPC;
   if (cb0 >= nbt) return;
   const BucketFn* fn = b.fn + p;
@@ -881,18 +882,20 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
     const uint32_t B0 = sbo[q], n = sbo[q + 1] - B0;
     const FineFn ff = make_fine<NFINE>(fn, cb, nsub);
 #if B200REF_FIN_PF != 0
-    if (q + 1 < FIN_BPC && cb + 1 < nbt) {
+    if (tid >= FIN_NT - 32 && q + 1 < FIN_BPC && cb + 1 < nbt) {
+      // the last warp (the one most often idle in a bucket's tail) issues one prefetch per 128-byte line of
+      // the next bucket's keys and positions, and of its bucket function
+      const uint32_t lane = tid & 31;
       const uint32_t nB0 = sbo[q + 1], nn = min(sbo[q + 2] - nB0, (uint32_t)CAP1);
-      // one prefetch per 128-byte line of the next bucket's keys and positions, and of its bucket function
       const uintptr_t ka = (uintptr_t)(pk0 + nB0), ke = ka + (size_t)nn * 8;
       const uintptr_t ia = (uintptr_t)(pi0 + nB0), ie = ia + (size_t)nn * 4;
       const uint32_t nlk = nn ? (uint32_t)(((ke - 1) >> 7) - (ka >> 7)) + 1u : 0u;
       const uint32_t nli = nn ? (uint32_t)(((ie - 1) >> 7) - (ia >> 7)) + 1u : 0u;
-      for (uint32_t l = tid; l < nlk + nli; l += FIN_NT)
+      for (uint32_t l = lane; l < nlk + nli; l += 32)
         prefetch_line((const void*)(l < nlk ? ((ka >> 7) + l) << 7 : ((ia >> 7) + (l - nlk)) << 7));
       const int c1 = (cb + 1) >> sh;
-      if (tid == FIN_NT - 1) prefetch_line(&fn->fsub[c1]);
-      if (tid == FIN_NT - 2 && c1 > 0) prefetch_line(&fn->sp[c1 - 1]);
+      if (lane == 0) prefetch_line(&fn->fsub[c1]);
+      if (lane == 1 && c1 > 0) prefetch_line(&fn->sp[c1 - 1]);
     }
 #endif
     if (n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big

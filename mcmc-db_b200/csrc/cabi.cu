@@ -436,7 +436,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
     else
       LAUNCH(K_PARTITION, st, k_partition_w<<<gc, PART_NT, sizeof(WideSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
-    LAUNCH(K_FINISH, st, k_finish<<<dim3((nb1 * nsub + FIN_BPC - 1) / FIN_BPC, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
+    LAUNCH(K_FINISH, st, k_finish<<<dim3((nb1 * nsub + FIN_BPC - 1) / FIN_BPC, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, nsub, nb1 * nsub, bb, FinishOut{rank_b_batch}));
     LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
     CUDA_TRY(cudaStreamWaitEvent(st, side_stream(slot).join, 0));
 

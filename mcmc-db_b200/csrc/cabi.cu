@@ -479,8 +479,12 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       cs.wl[1] = (int*)(wb + L.cwl1);
       cs.nwl = (int*)(wb + L.cnwl);
       CUDA_TRY(cudaMemsetAsync(cs.nwl, 0, 2 * sizeof(int), st));
-      if (g.nunits)
-        LAUNCH(K_CHAIN, st, k_moments0<<<dim3((unsigned)(C * g.nunits), PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, cs.part));
+      if (g.nunits) {
+        // units per CTA: about MO_CTA_TILES sub-tiles of work behind one exposed first copy
+        const uint32_t upc = std::max<uint32_t>(1u, MO_CTA_TILES / g.tpu);
+        const unsigned gx = (unsigned)((C * g.nunits + upc - 1) / upc);
+        LAUNCH(K_CHAIN, st, k_moments0<<<dim3(gx, PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, upc, cs.part));
+      }
       LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
       int cur = 0;
       for (uint32_t t0 = 1 + LAGB; t0 < (uint32_t)N; t0 += LAGR) {

@@ -31,7 +31,14 @@ constexpr int LAGB = 16;                 // lags per thread block half; round 0 
 constexpr int LAGR = 2 * LAGB;           // lags per later round (the two CTA halves take 16 each)
 constexpr int CHUNK = 16;                // consecutive draws per thread step
 constexpr int MO_SUB = MO_NT * CHUNK;    // 2048 draws per sub-tile
-constexpr int MO_UNIT_TILES = 4;        // a unit (one CTA) covers at most 4 sub-tiles = 8192 draws
+#ifndef B200REF_MO_UNIT_TILES
+#define B200REF_MO_UNIT_TILES 8
+#endif
+constexpr int MO_UNIT_TILES = B200REF_MO_UNIT_TILES;  // a unit (one CTA) covers at most this many sub-tiles
+#ifndef B200REF_MO_CTA_TILES
+#define B200REF_MO_CTA_TILES 12
+#endif
+constexpr int MO_CTA_TILES = B200REF_MO_CTA_TILES;  // sub-tiles one round-0 CTA streams (several units)
 constexpr int MO_VALS = LAGB + 10;       // per (unit, kind) in round 0: 16 lag sums + 2 x {sum, sq, first, differs, present}
 constexpr int DEC_NT = 64;
 
@@ -136,119 +143,143 @@ struct Mo0Smem {
   uint64_t bar;
 };
 
-__global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restrict__ zz, ChainGeom g, double* part) {
+// upc consecutive units of one parameter per CTA (units of a parameter are adjacent in memory): the copy of
+// a unit's first sub-tile is issued while the previous unit's last sub-tile is still being accumulated, so
+// only the CTA's very first copy is exposed (a chain of 4096 draws is just two sub-tiles).
+__global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restrict__ zz, ChainGeom g, uint32_t upc, double* part) {
   extern __shared__ __align__(128) unsigned char mo_smem_raw[];
   Mo0Smem& S = *reinterpret_cast<Mo0Smem*>(mo_smem_raw);
   const int p = blockIdx.y;
-  const uint32_t c = blockIdx.x / g.nunits, u = blockIdx.x % g.nunits;
   const int tid = threadIdx.x, lane = tid & 31;
   const int kind = tid >> 7, ct = tid & (MO_NT - 1), wp = ct >> 5;
-  uint32_t a, b;
-  unit_range(g, u, a, b);
-  const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
+  const uint32_t unit0 = blockIdx.x * upc, unit1 = min(unit0 + upc, g.C * g.nunits);
+  const double2* zp = zz + (size_t)p * g.C * g.N;
   if (tid == 0) {
     mbar_init(&S.bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0 && a < b) stage_pairs(S.raw, zc + a, min((uint32_t)MO_RAW0, g.N - a), &S.bar);
+  // every unit is non-empty: its first sub-tile starts below N (chain_geom)
+  auto unit_start = [&](uint32_t unit, uint32_t& c, uint32_t& a, uint32_t& b) {
+    c = unit / g.nunits;
+    unit_range(g, unit % g.nunits, a, b);
+  };
+  if (tid == 0 && unit0 < unit1) {
+    uint32_t c, a, b;
+    unit_start(unit0, c, a, b);
+    stage_pairs(S.raw, zp + (size_t)c * g.N + a, min((uint32_t)MO_RAW0, g.N - a), &S.bar);
+  }
   const uint32_t half = g.half, two = 2 * g.half;
-  // first draw of this unit in each half (if any)
-  const bool has1 = a < half, has2 = b > half && max(a, half) < two;
-  double f1 = 0.0, f2 = 0.0;
-  if (has1) { const double2 f = zc[a]; f1 = kind ? f.y : f.x; }
-  if (has2) { const double2 f = zc[max(a, half)]; f2 = kind ? f.y : f.x; }
-  double acc[LAGB];
-#pragma unroll
-  for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
-  double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0;
-  bool d1 = false, d2 = false;
   uint32_t phase = 0, buf = 0;
-  for (uint32_t sub = a; sub < b; sub += MO_SUB, buf ^= 1u) {
-    const uint32_t len = min((uint32_t)MO_SUB, b - sub);
-    const uint32_t nel = min((uint32_t)MO_RAW0, g.N - sub);  // pairs the copy delivered; the rest reads as 0
-    mbar_wait(&S.bar, phase);
-    phase ^= 1u;
-    double* y0 = S.y[buf][0];
-    double* y1 = S.y[buf][1];
+  for (uint32_t unit = unit0; unit < unit1; ++unit) {
+    uint32_t c, a, b;
+    unit_start(unit, c, a, b);
+    const double2* zc = zp + (size_t)c * g.N;
+    // first draw of this unit in each half (if any): read from the staged tiles when they arrive
+    const bool has1 = a < half, has2 = b > half && max(a, half) < two;
+    const uint32_t pos2 = max(a, half);
+    double f1 = 0.0, f2 = 0.0;
+    double acc[LAGB];
 #pragma unroll
-    for (int it = 0; it < MO_SUB / MO_CTA; ++it) {
-      const uint32_t i = it * MO_CTA + tid;
-      const double2 v = (i < nel) ? S.raw[i] : make_double2(0.0, 0.0);
-      y0[pad_idx(i)] = v.x;
-      y1[pad_idx(i)] = v.y;
-    }
-    if (tid < MO_HALO0) {
-      const uint32_t i = MO_SUB + tid;
-      const double2 v = (i < nel) ? S.raw[i] : make_double2(0.0, 0.0);
-      y0[pad_idx(i)] = v.x;
-      y1[pad_idx(i)] = v.y;
-    }
-    __syncthreads();  // tiles complete, staging buffer free; buffer buf^1 was last read before this barrier
-    if (tid == 0 && sub + MO_SUB < b)
-      stage_pairs(S.raw, zc + sub + MO_SUB, min((uint32_t)MO_RAW0, g.N - (sub + MO_SUB)), &S.bar);
-    const uint32_t i0 = ct * CHUNK;
-    if (i0 < len) {
-      const uint32_t nvalid = min((uint32_t)CHUNK, len - i0);
-      const uint32_t g0 = sub + i0;
-      double w[2 * CHUNK];
-      const double* gb = &S.y[buf][kind][ct * (CHUNK + 2)];
-      load16(gb, w);
-      load16(gb + CHUNK + 2, w + CHUNK);
-      const bool in1 = g0 + CHUNK <= half, in2 = g0 >= half && g0 + CHUNK <= two;
-      if (nvalid == CHUNK && (in1 || in2)) {
-        const double fr = in1 ? f1 : f2;
-        double ls = 0.0, lq = 0.0;
-        bool ld = false;
+    for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
+    double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0;
+    bool d1 = false, d2 = false;
+    for (uint32_t sub = a; sub < b; sub += MO_SUB, buf ^= 1u) {
+      const uint32_t len = min((uint32_t)MO_SUB, b - sub);
+      const uint32_t nel = min((uint32_t)MO_RAW0, g.N - sub);  // pairs the copy delivered; the rest reads as 0
+      mbar_wait(&S.bar, phase);
+      phase ^= 1u;
+      double* y0 = S.y[buf][0];
+      double* y1 = S.y[buf][1];
 #pragma unroll
-        for (int s = 0; s < CHUNK; ++s) {
-          const double v = w[s];
-          ls += v;
-          lq = fma(v, v, lq);
-          ld |= (v != fr);
-#pragma unroll
-          for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + 1 + l], acc[l]);
+      for (int it = 0; it < MO_SUB / MO_CTA; ++it) {
+        const uint32_t i = it * MO_CTA + tid;
+        const double2 v = (i < nel) ? S.raw[i] : make_double2(0.0, 0.0);
+        y0[pad_idx(i)] = v.x;
+        y1[pad_idx(i)] = v.y;
+      }
+      if (tid < MO_HALO0) {
+        const uint32_t i = MO_SUB + tid;
+        const double2 v = (i < nel) ? S.raw[i] : make_double2(0.0, 0.0);
+        y0[pad_idx(i)] = v.x;
+        y1[pad_idx(i)] = v.y;
+      }
+      __syncthreads();  // tiles complete, staging buffer free; buffer buf^1 was last read before this barrier
+      if (tid == 0) {
+        if (sub + MO_SUB < b) {
+          stage_pairs(S.raw, zc + sub + MO_SUB, min((uint32_t)MO_RAW0, g.N - (sub + MO_SUB)), &S.bar);
+        } else if (unit + 1 < unit1) {
+          uint32_t cn, an, bn;
+          unit_start(unit + 1, cn, an, bn);
+          stage_pairs(S.raw, zp + (size_t)cn * g.N + an, min((uint32_t)MO_RAW0, g.N - an), &S.bar);
         }
-        if (in1) { s1 += ls; q1 += lq; d1 |= ld; } else { s2 += ls; q2 += lq; d2 |= ld; }
-      } else {
+      }
+      if (sub == a && has1) f1 = S.y[buf][kind][0];
+      if (has2 && pos2 >= sub && pos2 < sub + len) f2 = S.y[buf][kind][pad_idx(pos2 - sub)];
+      const uint32_t i0 = ct * CHUNK;
+      if (i0 < len) {
+        const uint32_t nvalid = min((uint32_t)CHUNK, len - i0);
+        const uint32_t g0 = sub + i0;
+        double w[2 * CHUNK];
+        const double* gb = &S.y[buf][kind][ct * (CHUNK + 2)];
+        load16(gb, w);
+        load16(gb + CHUNK + 2, w + CHUNK);
+        const bool in1 = g0 + CHUNK <= half, in2 = g0 >= half && g0 + CHUNK <= two;
+        if (nvalid == CHUNK && (in1 || in2)) {
+          const double fr = in1 ? f1 : f2;
+          double ls = 0.0, lq = 0.0;
+          bool ld = false;
 #pragma unroll
-        for (int s = 0; s < CHUNK; ++s) {
-          const bool ok = (uint32_t)s < nvalid;
-          const double v = ok ? w[s] : 0.0;
-          const uint32_t gi = g0 + s;
-          if (ok && gi < half) { s1 += v; q1 = fma(v, v, q1); d1 |= (v != f1); }
-          else if (ok && gi < two) { s2 += v; q2 = fma(v, v, q2); d2 |= (v != f2); }
+          for (int s = 0; s < CHUNK; ++s) {
+            const double v = w[s];
+            ls += v;
+            lq = fma(v, v, lq);
+            ld |= (v != fr);
 #pragma unroll
-          for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + 1 + l], acc[l]);
+            for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + 1 + l], acc[l]);
+          }
+          if (in1) { s1 += ls; q1 += lq; d1 |= ld; } else { s2 += ls; q2 += lq; d2 |= ld; }
+        } else {
+#pragma unroll
+          for (int s = 0; s < CHUNK; ++s) {
+            const bool ok = (uint32_t)s < nvalid;
+            const double v = ok ? w[s] : 0.0;
+            const uint32_t gi = g0 + s;
+            if (ok && gi < half) { s1 += v; q1 = fma(v, v, q1); d1 |= (v != f1); }
+            else if (ok && gi < two) { s2 += v; q2 = fma(v, v, q2); d2 |= (v != f2); }
+#pragma unroll
+            for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + 1 + l], acc[l]);
+          }
         }
       }
     }
-  }
-  // unit totals: 16 lag sums by the halving reduce, the half statistics by butterflies
-  const double tot = warp_reduce_16(*reinterpret_cast<double (*)[16]>(acc));
+    // unit totals: 16 lag sums by the halving reduce, the half statistics by butterflies
+    const double tot = warp_reduce_16(*reinterpret_cast<double (*)[16]>(acc));
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(FULL, s1, o);
-    q1 += __shfl_xor_sync(FULL, q1, o);
-    s2 += __shfl_xor_sync(FULL, s2, o);
-    q2 += __shfl_xor_sync(FULL, q2, o);
-  }
-  const bool w1 = __any_sync(FULL, d1), w2 = __any_sync(FULL, d2);
-  double* r = S.red[kind][wp];
-  if (lane < LAGB) r[lane] = tot;
-  if (lane == 0) {
-    r[16] = s1; r[17] = q1; r[18] = f1; r[19] = w1 ? 1.0 : 0.0; r[20] = has1 ? 1.0 : 0.0;
-    r[21] = s2; r[22] = q2; r[23] = f2; r[24] = w2 ? 1.0 : 0.0; r[25] = has2 ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  if (ct < MO_VALS) {
-    double v = S.red[kind][0][ct];
-    const bool copy = (ct == 18 || ct == 20 || ct == 23 || ct == 25);  // first values / presence: not summed
-    if (!copy) {
-#pragma unroll
-      for (int k = 1; k < MO_NT / 32; ++k) v += S.red[kind][k][ct];
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(FULL, s1, o);
+      q1 += __shfl_xor_sync(FULL, q1, o);
+      s2 += __shfl_xor_sync(FULL, s2, o);
+      q2 += __shfl_xor_sync(FULL, q2, o);
     }
-    part[((((size_t)p * g.C + c) * g.nunits + u) * 2 + kind) * MO_VALS + ct] = v;
+    const bool w1 = __any_sync(FULL, d1), w2 = __any_sync(FULL, d2);
+    double* r = S.red[kind][wp];
+    if (lane < LAGB) r[lane] = tot;
+    if (lane == 0) {
+      r[16] = s1; r[17] = q1; r[18] = f1; r[19] = w1 ? 1.0 : 0.0; r[20] = has1 ? 1.0 : 0.0;
+      r[21] = s2; r[22] = q2; r[23] = f2; r[24] = w2 ? 1.0 : 0.0; r[25] = has2 ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (ct < MO_VALS) {
+      double v = S.red[kind][0][ct];
+      const bool copy = (ct == 18 || ct == 20 || ct == 23 || ct == 25);  // first values / presence: not summed
+      if (!copy) {
+#pragma unroll
+        for (int k = 1; k < MO_NT / 32; ++k) v += S.red[kind][k][ct];
+      }
+      part[(((size_t)p * g.C * g.nunits + unit) * 2 + kind) * MO_VALS + ct] = v;
+    }
+    // (S.red is next written after the next unit's tile barriers)
   }
 }
 

@@ -17,6 +17,43 @@ from .convert import _compute_diagnostics
 from .store import PackagedStore
 
 
+def list_models(store=None) -> list[str]:
+    """reference.py:15-17"""
+    return (store or PackagedStore()).list_models()
+
+
+def draws(
+    model: str,
+    params: Sequence[str] | None = None,
+    chains: Sequence[int] | None = None,
+    return_: str = "arrow",
+    store=None,
+):
+    """Reference draws of a model (reference.py:51-73).  ``return_``: ``"arrow"`` (table / reader),
+    ``"numpy"`` ([rows, P], parameter fastest, like ``Draws.to_numpy`` draws.py:20-29), ``"list"`` (row dicts),
+    and -- new -- ``"device"``: the CUDA tensor ``[P, C, N]`` the batched kernels consume, rows verified /
+    ordered by (chain, draw) on the device (``ingest.table_to_device``)."""
+    store = store or PackagedStore()
+    reader = store.open_draws(model, params=params, chains=chains)
+    if return_ == "arrow" and params is not None:
+        return reader
+    table = reader.read_all() if hasattr(reader, "read_all") else reader
+    names = list(params) if params is not None else [c for c in table.column_names if c not in {"chain", "draw"}]
+    if return_ == "arrow":
+        return table
+    if return_ == "numpy":
+        import numpy as np
+
+        return np.stack([table.column(p).to_numpy(zero_copy_only=False) for p in names], axis=-1)
+    if return_ == "list":
+        return table.to_pylist()
+    if return_ == "device":
+        from .ingest import table_to_device
+
+        return table_to_device(table, names)[0]
+    raise ValueError(f"Unknown return type: {return_}")
+
+
 def stan_data(model: str, store=None) -> dict:
     """reference.py:20-22"""
     return (store or PackagedStore()).read_stan_data(model)

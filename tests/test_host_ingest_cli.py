@@ -94,3 +94,31 @@ def test_cli_list_and_info_need_no_device(tmp_path, monkeypatch):
     assert res.exit_code == 0 and json.loads(res.output) == {"model": "example"}
     res = runner.invoke(main, ["stats", "example", "--backend", "numpy"])
     assert res.exit_code == 2  # click rejects backends this build does not register
+
+
+def test_reference_api_surface_without_device(tmp_path):
+    """list_models / draws / stan_data / model_code of the reference's Python API (reference.py:15-73;
+    reference test: tests/unit/test_reference.py:13-84) through the packaged layout, no device needed."""
+    from mcmc_ref_b200 import reference
+    from mcmc_ref_b200.store import PackagedStore
+
+    for sub in ("draws", "meta", "stan_data", "stan_models"):
+        (tmp_path / sub).mkdir()
+    _write_draws_parquet(tmp_path / "draws" / "m.draws.parquet")
+    (tmp_path / "stan_data" / "m.data.json").write_text(json.dumps({"N": 2, "y": [1.0, 2.0]}))
+    (tmp_path / "stan_models" / "m.stan").write_text("model { }\n")
+    store = PackagedStore(packaged_root=tmp_path, local_root=tmp_path / "none")
+    assert reference.list_models(store=store) == ["m"]
+    assert reference.stan_data("m", store=store) == {"N": 2, "y": [1.0, 2.0]}
+    assert reference.model_code("m", store=store).startswith("model")
+    a = reference.draws("m", return_="numpy", store=store)
+    assert a.shape == (8, 1) and a[1, 0] == 2.0
+    t = reference.draws("m", params=["mu"], chains=[1, 3], return_="arrow", store=store).read_all()
+    assert t.num_rows == 4 and set(t.column("chain").to_pylist()) == {1, 3}
+    assert reference.draws("m", return_="list", store=store)[0] == {"chain": 0, "draw": 0, "mu": 1.0}
+    with pytest.raises(ValueError, match="Unknown return type"):
+        reference.draws("m", return_="frame", store=store)
+    with pytest.raises(FileNotFoundError, match="draws not found for model"):
+        reference.draws("absent", store=store)
+    with pytest.raises(FileNotFoundError, match="stan data not found"):
+        reference.stan_data("absent", store=store)

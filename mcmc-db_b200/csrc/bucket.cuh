@@ -34,7 +34,10 @@ constexpr int NFINE_BIG = 2048;
 constexpr int FINB_NT = 1024;
 constexpr int BIGLIST_PER_PARAM = 256;  // every coarse bucket of a parameter may be oversize (heavy ties)
 constexpr int CAP1 = 2048;        // draws a coarse bucket may hold (on-chip capacity of k_finish)
-constexpr int OVERSAMPLE = 16;    // samples per coarse bucket
+#ifndef B200REF_OVERSAMPLE
+#define B200REF_OVERSAMPLE 16
+#endif
+constexpr int OVERSAMPLE = B200REF_OVERSAMPLE;    // samples per coarse bucket
 constexpr int CHUNK_P = 4096;     // draws per partition chunk
 constexpr int PART_NT = 256;
 constexpr int PART_IPT = CHUNK_P / PART_NT;

@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restric
         load16(gb + CHUNK + 2, w + CHUNK);
         const bool in1 = g0 + CHUNK <= half, in2 = g0 >= half && g0 + CHUNK <= two;
         if (nvalid == CHUNK && (in1 || in2)) {
-          const double fr = in1 ? f1 : f2;
+          // "differs from the half's first draw" on the bit patterns (integer pipe): scores are table entries,
+          // equal values are equal bits (the table's only zero is +0.0)
+          const long long frb = __double_as_longlong(in1 ? f1 : f2);
           double ls = 0.0, lq = 0.0;
           bool ld = false;
 #pragma unroll
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restric
             const double v = w[s];
             ls += v;
             lq = fma(v, v, lq);
-            ld |= (v != fr);
+            ld |= (__double_as_longlong(v) != frb);
 #pragma unroll
             for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + 1 + l], acc[l]);
           }

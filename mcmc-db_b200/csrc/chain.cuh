@@ -5,10 +5,11 @@
 //   with first-negative truncation -> ESS   (_ess :154-177, _autocorr :180-193)
 //
 // Streaming design.  zz[p][c][i] = {z_bulk, z_folded}.  Every chain is cut into units
-// (pieces of one half-chain, <= 8192 draws); a 128-thread CTA streams its unit through
+// (runs of <= 8 sub-tiles of one chain); a CTA streams its units through
 // shared memory in 2048-draw sub-tiles and accumulates, for both kinds at once,
-//   * sum, sum of squares, min, max of the unit (raw moments: z-scores have mean ~ 0 and
-//     variance ~ 1, so sum(y^2) - n*mean^2 loses no accuracy; min == max -> variance 0 exactly)
+//   * per half of the chain: sum, sum of squares and "some draw differs from the first" (raw
+//     moments: z-scores have mean ~ 0 and variance ~ 1, so sum(y^2) - n*mean^2 loses no accuracy;
+//     a constant half -> variance 0 exactly)
 //   * 16 raw lag products R_t = sum_i y_i * y_{i+t}, t = t0 .. t0+15, by a register
 //     sliding window (16 FMAs per 2 shared loads).
 // A small per-(parameter, kind) kernel turns the partial sums into chain means / variances,
@@ -16,7 +17,7 @@
 //     S_t = R_t - mean * (2*total - head_t - tail_t) + (n - t) * mean^2 ,
 // and walks rho_1, rho_2, ... until the first negative one (diagnostics.py:172-176).
 // Pairs whose rho is still positive after 16 lags go onto a work list; further rounds
-// stream only those chains with t0 advanced by 16.  Well-mixed chains finish in round 0,
+// stream only those chains, 32 lags per round.  Well-mixed chains finish in round 0,
 // and no chain length limit remains (nothing has to fit on-chip).
 // Because all chains of a parameter have the same length n, sum_c cov_c / (n - t) is
 // accumulated as (sum_c S_c) / (n - t).

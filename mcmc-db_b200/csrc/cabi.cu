@@ -337,6 +337,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     CUDA_TRY(cudaFuncSetAttribute(k_finish_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemBig)));
     CUDA_TRY(cudaFuncSetAttribute(k_moments0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Mo0Smem)));
     CUDA_TRY(cudaFuncSetAttribute(k_moments_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoRSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(k_moments_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoR1Smem)));
     part_attr = true;
   }
 
@@ -493,7 +494,10 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
         CUDA_TRY(cudaStreamSynchronize(st));
         if (nwork == 0) break;
         CUDA_TRY(cudaMemsetAsync(cs.nwl + (cur ^ 1), 0, sizeof(int), st));
-        LAUNCH(K_CHAIN, st, k_moments_r<<<dim3((unsigned)(C * g.nunits), nwork), MO_CTA, sizeof(MoRSmem), st>>>(zz, g, t0, cs.wl[cur], cs.partr));
+        if (t0 <= (uint32_t)MO_T0MAX)
+          LAUNCH(K_CHAIN, st, k_moments_r1<<<dim3((unsigned)(C * g.nunits), nwork), MO_CTA, sizeof(MoR1Smem), st>>>(zz, g, t0, cs.wl[cur], cs.partr));
+        else
+          LAUNCH(K_CHAIN, st, k_moments_r<<<dim3((unsigned)(C * g.nunits), nwork), MO_CTA, sizeof(MoRSmem), st>>>(zz, g, t0, cs.wl[cur], cs.partr));
         LAUNCH(K_DECIDE, st, k_decide_r<<<nwork, DEC_NT, 0, st>>>(zz, g, PB, t0, cur, cs));
         cur ^= 1;
       }

@@ -378,6 +378,88 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments_r(const double2* __restri
   }
 }
 
+// ---------------------------------------------------------------- later rounds, near lags: ONE staged tile
+// While t0 is small against the sub-tile (t0 <= MO_T0MAX) the second factors y[i + t0 + ...] lie in the same
+// stretch of the chain as the first ones: one TMA copy of 2048 + t0 + 32 pairs and one de-interleave per
+// sub-tile instead of two of each (the two-tile kernel above measured L1-bound, 77 %).  t0 - 1 is a multiple
+// of 16 (t0 = 17 + 32 r), so a thread's second-factor window starts one draw after a 16-draw group boundary:
+// it loads the two groups from that boundary plus one draw and uses window[s + l + 1].
+constexpr int MO_T0MAX = 1 + LAGB + 32 * LAGR;                 // rounds 1 .. 33
+constexpr int MO_RAW1 = MO_SUB + MO_T0MAX + LAGR + CHUNK;      // pairs staged per sub-tile (upper bound)
+constexpr int MO_PAD1 = (MO_RAW1 / CHUNK + 2) * (CHUNK + 2);
+struct MoR1Smem {
+  double2 raw[MO_RAW1];
+  double y[MO_PAD1];
+  double red[2][MO_NT / 32][LAGB];
+  uint64_t bar;
+};
+
+__global__ void __launch_bounds__(MO_CTA, 2) k_moments_r1(const double2* __restrict__ zz, ChainGeom g, uint32_t t0,
+                                                          const int* __restrict__ wl, double* partr) {
+  extern __shared__ __align__(128) unsigned char mo_smem_raw[];
+  MoR1Smem& S = *reinterpret_cast<MoR1Smem*>(mo_smem_raw);
+  const int item = wl[blockIdx.y];
+  const int p = item >> 1, kind = item & 1;
+  const uint32_t c = blockIdx.x / g.nunits, u = blockIdx.x % g.nunits;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int hb = tid >> 7, ct = tid & (MO_NT - 1), wp = ct >> 5;  // hb: which block of 16 lags
+  uint32_t a, b;
+  unit_range(g, u, a, b);
+  const uint32_t lim = (g.N > t0) ? g.N - t0 : 0;  // first factors need i + t0 < N
+  b = min(b, lim);
+  const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
+  const uint32_t span = MO_SUB + t0 + LAGR + CHUNK;  // pairs a full sub-tile touches
+  if (tid == 0) {
+    mbar_init(&S.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  double acc[LAGB];
+#pragma unroll
+  for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
+  if (a < b && tid == 0) stage_pairs(S.raw, zc + a, min(span, g.N - a), &S.bar);
+  const uint32_t goff = (t0 - 1) / CHUNK + (uint32_t)hb;  // group offset of the second-factor window
+  uint32_t phase = 0;
+  for (uint32_t sub = a; sub < b; sub += MO_SUB) {
+    const uint32_t len = min((uint32_t)MO_SUB, b - sub);
+    const uint32_t nel = min(span, g.N - sub);                       // pairs the copy delivered; the rest reads as 0
+    const uint32_t need = min(span, len + t0 + LAGR + CHUNK);        // pairs this sub-tile's threads touch
+    mbar_wait(&S.bar, phase);
+    phase ^= 1u;
+    {
+      const double* rk = reinterpret_cast<const double*>(S.raw) + kind;
+      for (uint32_t i = tid; i < need; i += MO_CTA) S.y[pad_idx(i)] = (i < nel) ? rk[2 * i] : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0 && sub + MO_SUB < b) stage_pairs(S.raw, zc + sub + MO_SUB, min(span, g.N - (sub + MO_SUB)), &S.bar);
+    const uint32_t i0 = ct * CHUNK;
+    if (i0 < len) {
+      const uint32_t nvalid = min((uint32_t)CHUNK, len - i0);
+      double va[CHUNK], w[2 * CHUNK + 1];
+      load16(&S.y[ct * (CHUNK + 2)], va);
+      load16(&S.y[(ct + goff) * (CHUNK + 2)], w);
+      load16(&S.y[(ct + goff + 1) * (CHUNK + 2)], w + CHUNK);
+      w[2 * CHUNK] = S.y[(ct + goff + 2) * (CHUNK + 2)];
+#pragma unroll
+      for (int s = 0; s < CHUNK; ++s) {
+        const double v = ((uint32_t)s < nvalid) ? va[s] : 0.0;
+#pragma unroll
+        for (int l = 0; l < LAGB; ++l) acc[l] = fma(v, w[s + l + 1], acc[l]);
+      }
+    }
+    __syncthreads();
+  }
+  const double tot = warp_reduce_16(*reinterpret_cast<double (*)[16]>(acc));
+  if (lane < LAGB) S.red[hb][wp][lane] = tot;
+  __syncthreads();
+  if (ct < LAGB) {
+    double v = S.red[hb][0][ct];
+#pragma unroll
+    for (int k = 1; k < MO_NT / 32; ++k) v += S.red[hb][k][ct];
+    partr[(((size_t)blockIdx.y * g.C + c) * g.nunits + u) * LAGR + hb * LAGB + ct] = v;
+  }
+}
+
 constexpr int DEC_RED = LAGR + 2;
 // block-wide sums of n values (n <= DEC_RED) over DEC_NT = 64 threads, fixed order; result in out[] (shared)
 __device__ __forceinline__ void dec_reduce(double* vals, int n, double (*red)[DEC_RED], double* out) {

@@ -24,6 +24,13 @@
 #pragma once
 #include "common.cuh"
 
+// k_finish: what stays in registers across the fine-bucket scan.  0: key, position and (bucket, rank) word of
+// every draw (spills 3 words per draw at 40 registers); 1: the position is read again after the scan;
+// 2: key and position are both read again (L1 / L2 hits) and only the word stays -- no spills, 1.94 -> 1.71 ms.
+#ifndef B200REF_FIN_RELOAD_IDX
+#define B200REF_FIN_RELOAD_IDX 2
+#endif
+
 namespace b200ref {
 
 constexpr int NB1_MAX = 256;      // coarse buckets per parameter (power of two, <= 256)
@@ -533,17 +540,21 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
   const uint32_t* pi = b.pidx + (size_t)p * M + B0;
   if (!TWO_PASS) {
     double v[IPT];
-    uint32_t idx[IPT], r[IPT];
-    uint16_t f[IPT];
+    uint32_t fr[IPT];  // fine bucket | arrival rank in it << 16 (both below 2^16)
+#if !B200REF_FIN_RELOAD_IDX
+    uint32_t idx[IPT];
+#endif
 #pragma unroll
     for (int it = 0; it < IPT; ++it) {
       if ((uint32_t)(it * NT) >= n) break;  // uniform: typical buckets fill 2-4 of the IPT slots
       const uint32_t e = it * NT + tid;
       if (e < n) {
         v[it] = key2dbl(pk[e]);
+#if !B200REF_FIN_RELOAD_IDX
         idx[it] = pi[e];
-        f[it] = (uint16_t)fine(v[it]);
-        r[it] = atomicAdd(&sm.fh[f[it]], 1u);
+#endif
+        const uint32_t f = (uint32_t)fine(v[it]);
+        fr[it] = f | (atomicAdd(&sm.fh[f], 1u) << 16);
       }
     }
     __syncthreads();
@@ -554,9 +565,17 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
       if ((uint32_t)(it * NT) >= n) break;
       const uint32_t e = it * NT + tid;
       if (e < n) {
-        const uint32_t slot = sm.foff[f[it]] + r[it];
+        const uint32_t slot = sm.foff[fr[it] & 0xffffu] + (fr[it] >> 16);
+#if B200REF_FIN_RELOAD_IDX == 2
+        sm.kd[slot] = key2dbl(pk[e]);
+#else
         sm.kd[slot] = v[it];
+#endif
+#if B200REF_FIN_RELOAD_IDX
+        sm.i2[slot] = pi[e];  // read after the scan (the line is in L1 / L2): one register less per draw across it
+#else
         sm.i2[slot] = idx[it];
+#endif
       }
     }
   } else {
@@ -845,6 +864,9 @@ using FinSmemBig = FinSmem<CAPBIG, NFINE_BIG>;
 #ifndef B200REF_FIN_OCC
 #define B200REF_FIN_OCC 6
 #endif
+#ifndef B200REF_FIN_DUAL
+#define B200REF_FIN_DUAL 0
+#endif
 #ifndef B200REF_FIN_BPC
 #define B200REF_FIN_BPC 8
 #endif
@@ -902,7 +924,14 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
     }
 #endif
     if (n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
-      finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, ff, B0, n, M, p, b, fo);
+      // buckets of up to half the capacity (almost all of them when M / 256 <= ~700) keep their draws in
+      // registers across the scan without spilling; the full-capacity instantiation spills 3 words per draw
+#if B200REF_FIN_DUAL
+      if (n <= (uint32_t)(FIN_NT * FIN_IPT / 2))
+        finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT / 2, false>(sm, ff, B0, n, M, p, b, fo);
+      else
+#endif
+        finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, ff, B0, n, M, p, b, fo);
       __syncthreads();
     }
   }

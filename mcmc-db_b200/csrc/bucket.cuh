@@ -24,15 +24,26 @@
 #pragma once
 #include "common.cuh"
 
+// B200REF_FIN_LOAD2: keys loaded per group before their bucket functions run in k_finish (0 / 1: one by one).
 // k_finish: what stays in registers across the fine-bucket scan.  0: key, position and (bucket, rank) word of
 // every draw (spills 3 words per draw at 40 registers); 1: the position is read again after the scan;
 // 2: key and position are both read again (L1 / L2 hits) and only the word stays -- no spills, 1.94 -> 1.71 ms.
+#ifndef B200REF_BHIST_BATCH
+#define B200REF_BHIST_BATCH 1
+#endif
+#ifndef B200REF_BHIST_UNROLL
+#define B200REF_BHIST_UNROLL 2
+#endif
+#ifndef B200REF_FIN_LOAD2
+#define B200REF_FIN_LOAD2 2
+#endif
 #ifndef B200REF_FIN_RELOAD_IDX
 #define B200REF_FIN_RELOAD_IDX 2
 #endif
 
 namespace b200ref {
 
+constexpr int BHIST_UNROLL = B200REF_BHIST_UNROLL;  // draws in flight per thread in k_bhist
 constexpr int NB1_MAX = 256;      // coarse buckets per parameter (power of two, <= 256)
 constexpr int NCELL = 1024;       // linear cells of the splitter lookup table
 constexpr int NFINE = 512;        // fine buckets per coarse bucket
@@ -217,7 +228,10 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
 }
 
 // ---------------------------------------------------------------- k_bhist
-__global__ void __launch_bounds__(PART_NT) k_bhist(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
+#ifndef B200REF_BHIST_OCC
+#define B200REF_BHIST_OCC 8
+#endif
+__global__ void __launch_bounds__(PART_NT, B200REF_BHIST_OCC) k_bhist(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
                                                     BucketBufs b) {
   __shared__ double sp[NB1_MAX];
   __shared__ uint16_t lut[NCELL + 2];
@@ -235,7 +249,39 @@ __global__ void __launch_bounds__(PART_NT) k_bhist(const double* __restrict__ x,
   uint32_t* meta = b.bmeta + (size_t)p * M;
   double s1 = 0.0, s2 = 0.0;
   bool bad = false;
-#pragma unroll 4
+#if B200REF_BHIST_BATCH
+  // explicit batches: BHIST_UNROLL loads, then their bucket functions, then their (returning) atomics, then
+  // the stores -- so that several draws' memory round trips overlap per thread
+#pragma unroll 1
+  for (int it0 = 0; it0 < PART_IPT; it0 += BHIST_UNROLL) {
+    double v[BHIST_UNROLL];
+    uint32_t c[BHIST_UNROLL], r[BHIST_UNROLL];
+#pragma unroll
+    for (int j = 0; j < BHIST_UNROLL; ++j) {
+      const uint32_t e = base + (it0 + j) * PART_NT + threadIdx.x;
+      v[j] = (e < M) ? xp[e] : c0;
+    }
+#pragma unroll
+    for (int j = 0; j < BHIST_UNROLL; ++j) c[j] = (uint32_t)coarse_of(v[j], lo, cs, sp, lut);
+#pragma unroll
+    for (int j = 0; j < BHIST_UNROLL; ++j) {
+      const uint32_t e = base + (it0 + j) * PART_NT + threadIdx.x;
+      r[j] = (e < M) ? atomicAdd(&cnt[c[j]], 1u) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < BHIST_UNROLL; ++j) {
+      const uint32_t e = base + (it0 + j) * PART_NT + threadIdx.x;
+      if (e < M) {
+        bad |= !is_finite_bits(v[j]);
+        const double d = v[j] - c0;
+        s1 += d;
+        s2 = fma(d, d, s2);
+        meta[e] = (c[j] << 16) | r[j];
+      }
+    }
+  }
+#else
+#pragma unroll BHIST_UNROLL
   for (int it = 0; it < PART_IPT; ++it) {
     const uint32_t e = base + it * PART_NT + threadIdx.x;
     if (e < M) {
@@ -250,6 +296,7 @@ __global__ void __launch_bounds__(PART_NT) k_bhist(const double* __restrict__ x,
       meta[e] = (c << 16) | atomicAdd(&cnt[c], 1u);
     }
   }
+#endif
   // deterministic block sums (fixed tree)
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -538,12 +585,32 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
   __syncthreads();
   const uint64_t* pk = b.pkey + (size_t)p * M + B0;
   const uint32_t* pi = b.pidx + (size_t)p * M + B0;
-  if (!TWO_PASS) {
+  if constexpr (!TWO_PASS) {
+#if !(B200REF_FIN_LOAD2 && B200REF_FIN_RELOAD_IDX == 2)
     double v[IPT];
+#endif
     uint32_t fr[IPT];  // fine bucket | arrival rank in it << 16 (both below 2^16)
 #if !B200REF_FIN_RELOAD_IDX
     uint32_t idx[IPT];
 #endif
+#if B200REF_FIN_LOAD2 && B200REF_FIN_RELOAD_IDX == 2
+    // keys in groups of FIN_LB: all loads of a group are in flight before the first bucket function needs its key
+    constexpr int LB = (IPT % B200REF_FIN_LOAD2 == 0) ? B200REF_FIN_LOAD2 : 1;
+#pragma unroll
+    for (int it = 0; it < IPT; it += LB) {
+      if ((uint32_t)(it * NT) >= n) break;  // uniform: typical buckets fill 2-4 of the IPT slots
+      uint64_t kk[LB];
+#pragma unroll
+      for (int j = 0; j < LB; ++j) kk[j] = pk[min((uint32_t)((it + j) * NT + tid), n - 1)];
+#pragma unroll
+      for (int j = 0; j < LB; ++j) {
+        if ((uint32_t)((it + j) * NT + tid) < n) {
+          const uint32_t f = (uint32_t)fine(key2dbl(kk[j]));
+          fr[it + j] = f | (atomicAdd(&sm.fh[f], 1u) << 16);
+        }
+      }
+    }
+#else
 #pragma unroll
     for (int it = 0; it < IPT; ++it) {
       if ((uint32_t)(it * NT) >= n) break;  // uniform: typical buckets fill 2-4 of the IPT slots
@@ -557,9 +624,33 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
         fr[it] = f | (atomicAdd(&sm.fh[f], 1u) << 16);
       }
     }
+#endif
     __syncthreads();
     fine_scan<NT, NF, CAP>(sm);
     __syncthreads();
+#if B200REF_FIN_LOAD2 && B200REF_FIN_RELOAD_IDX == 2
+    // keys and positions are read again (L1 / L2 hits), in the same groups, and go to their slots
+#pragma unroll
+    for (int it = 0; it < IPT; it += LB) {
+      if ((uint32_t)(it * NT) >= n) break;
+      uint64_t kk[LB];
+      uint32_t ii[LB];
+#pragma unroll
+      for (int j = 0; j < LB; ++j) {
+        const uint32_t e = min((uint32_t)((it + j) * NT + tid), n - 1);
+        kk[j] = pk[e];
+        ii[j] = pi[e];
+      }
+#pragma unroll
+      for (int j = 0; j < LB; ++j) {
+        if ((uint32_t)((it + j) * NT + tid) < n) {
+          const uint32_t slot = sm.foff[fr[it + j] & 0xffffu] + (fr[it + j] >> 16);
+          sm.kd[slot] = key2dbl(kk[j]);
+          sm.i2[slot] = ii[j];
+        }
+      }
+    }
+#else
 #pragma unroll
     for (int it = 0; it < IPT; ++it) {
       if ((uint32_t)(it * NT) >= n) break;
@@ -578,6 +669,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
 #endif
       }
     }
+#endif
   } else {
     for (uint32_t e = tid; e < n; e += NT) atomicAdd(&sm.fh[fine(key2dbl(pk[e]))], 1u);
     __syncthreads();

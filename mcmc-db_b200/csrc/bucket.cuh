@@ -325,11 +325,17 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
   if (t == 0) over = 0;
   __syncthreads();
   uint32_t* cnt = b.cnt + (size_t)p * nchunks * NB1_MAX;
+  // (loads in groups of 8 ahead of the stores: the compiler cannot hoist them across stores to the same array)
   uint32_t run = 0;
-  for (uint32_t c = 0; c < nchunks; ++c) {
-    const uint32_t v = cnt[(size_t)c * NB1_MAX + t];
-    cnt[(size_t)c * NB1_MAX + t] = run;
-    run += v;
+  for (uint32_t c0 = 0; c0 < nchunks; c0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < nchunks) ? cnt[(size_t)(c0 + j) * NB1_MAX + t] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c0 + j < nchunks) cnt[(size_t)(c0 + j) * NB1_MAX + t] = run;
+      run += v[j];
+    }
   }
   if (run > (uint32_t)CAPBIG) {
     over = 1;
@@ -354,7 +360,14 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
   const uint32_t excl = pre + incl - run;
   b.boff[(size_t)p * b.bstride + t] = excl;
   if (t == NB1_MAX - 1) b.boff[(size_t)p * b.bstride + NB1_MAX] = excl + run;
-  for (uint32_t c = 0; c < nchunks; ++c) cnt[(size_t)c * NB1_MAX + t] += excl;
+  for (uint32_t c0 = 0; c0 < nchunks; c0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < nchunks) ? cnt[(size_t)(c0 + j) * NB1_MAX + t] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < nchunks) cnt[(size_t)(c0 + j) * NB1_MAX + t] = v[j] + excl;
+  }
   if (t == 0) {
     // mean = c0 + S1/M ; var = (S2 - S1^2/M)/M  (sums about the sample median: no cancellation)
     double s1 = 0.0, s2 = 0.0;
@@ -797,16 +810,27 @@ __global__ void __launch_bounds__(PART_NT) k_bhist_w(const double* __restrict__ 
   const uint32_t base = chunk * CHUNK_P;
   double s1 = 0.0, s2 = 0.0;
   bool bad = false;
-#pragma unroll 4
-  for (int it = 0; it < PART_IPT; ++it) {
-    const uint32_t e = base + it * PART_NT + threadIdx.x;
-    if (e < M) {
-      const double v = xp[e];
-      bad |= !is_finite_bits(v);
-      const double d = v - c0;
-      s1 += d;
-      s2 = fma(d, d, s2);
-      atomicAdd(&sm.cnt[wide_of(v, lo, cs, sm, sub)], 1u);
+#pragma unroll 1
+  for (int it0 = 0; it0 < PART_IPT; it0 += 2) {  // pairs of draws in flight, as in k_bhist
+    double v[2];
+    int c[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t e = base + (it0 + j) * PART_NT + threadIdx.x;
+      v[j] = (e < M) ? xp[e] : c0;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[j] = wide_of(v[j], lo, cs, sm, sub);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t e = base + (it0 + j) * PART_NT + threadIdx.x;
+      if (e < M) {
+        bad |= !is_finite_bits(v[j]);
+        const double d = v[j] - c0;
+        s1 += d;
+        s2 = fma(d, d, s2);
+        atomicAdd(&sm.cnt[c[j]], 1u);
+      }
     }
   }
   s1 = warp_sum(s1);

@@ -400,7 +400,11 @@ struct PartSmem {
 #ifndef B200REF_PART_OCC
 #define B200REF_PART_OCC 3
 #endif
-constexpr int PART_HB = PART_IPT / 2;  // draws per thread and load batch
+#ifndef B200REF_PART_NB
+#define B200REF_PART_NB 2
+#endif
+constexpr int PART_NB = B200REF_PART_NB;          // load batches per chunk
+constexpr int PART_HB = PART_IPT / PART_NB;  // draws per thread and load batch
 
 // One CTA per 4096-draw chunk: the (bucket, arrival rank) word k_bhist left for every draw gives its slot
 // in the chunk's bucket-ordered staging tile directly; the tile then leaves in runs (coalesced stores).
@@ -448,11 +452,11 @@ __global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const d
   }
   __syncthreads();
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (h == 1) {
+  for (int h = 0; h < PART_NB; ++h) {
+    if (h >= 1) {
 #pragma unroll
       for (int it = 0; it < PART_HB; ++it) {
-        const uint32_t e = min((PART_HB + it) * PART_NT + tid, n - 1);
+        const uint32_t e = min((h * PART_HB + it) * PART_NT + tid, n - 1);
         v[it] = xp[base + e];
         m[it] = meta[base + e];
       }

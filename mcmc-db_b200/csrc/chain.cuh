@@ -428,7 +428,20 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments_r1(const double2* __restr
     phase ^= 1u;
     {
       const double* rk = reinterpret_cast<const double*>(S.raw) + kind;
-      for (uint32_t i = tid; i < need; i += MO_CTA) S.y[pad_idx(i)] = (i < nel) ? rk[2 * i] : 0.0;
+      // groups of 4 reads ahead of their writes (the compiler keeps a load -> store order on shared memory)
+      for (uint32_t i0 = tid; i0 < need; i0 += 4 * MO_CTA) {
+        double t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = i0 + j * MO_CTA;
+          t[j] = (i < nel) ? rk[2 * i] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = i0 + j * MO_CTA;
+          if (i < need) S.y[pad_idx(i)] = t[j];
+        }
+      }
     }
     __syncthreads();
     if (tid == 0 && sub + MO_SUB < b) stage_pairs(S.raw, zc + sub + MO_SUB, min(span, g.N - (sub + MO_SUB)), &S.bar);

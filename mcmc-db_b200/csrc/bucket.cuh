@@ -24,21 +24,14 @@
 #pragma once
 #include "common.cuh"
 
-// B200REF_FIN_LOAD2: keys loaded per group before their bucket functions run in k_finish (0 / 1: one by one).
-// k_finish: what stays in registers across the fine-bucket scan.  0: key, position and (bucket, rank) word of
-// every draw (spills 3 words per draw at 40 registers); 1: the position is read again after the scan;
-// 2: key and position are both read again (L1 / L2 hits) and only the word stays -- no spills, 1.94 -> 1.71 ms.
-#ifndef B200REF_BHIST_BATCH
-#define B200REF_BHIST_BATCH 1
-#endif
+// Tuning knobs (defaults are the measured optimum on B200, see profiles/README.md):
+//   B200REF_BHIST_UNROLL  draws in flight per thread in k_bhist (explicit groups)
+//   B200REF_FIN_LOAD2     keys loaded per group before their bucket functions run in k_finish
 #ifndef B200REF_BHIST_UNROLL
 #define B200REF_BHIST_UNROLL 2
 #endif
 #ifndef B200REF_FIN_LOAD2
 #define B200REF_FIN_LOAD2 2
-#endif
-#ifndef B200REF_FIN_RELOAD_IDX
-#define B200REF_FIN_RELOAD_IDX 2
 #endif
 
 namespace b200ref {
@@ -249,9 +242,11 @@ __global__ void __launch_bounds__(PART_NT, B200REF_BHIST_OCC) k_bhist(const doub
   uint32_t* meta = b.bmeta + (size_t)p * M;
   double s1 = 0.0, s2 = 0.0;
   bool bad = false;
-#if B200REF_BHIST_BATCH
-  // explicit batches: BHIST_UNROLL loads, then their bucket functions, then their (returning) atomics, then
-  // the stores -- so that several draws' memory round trips overlap per thread
+  // Every draw leaves its bucket and its arrival rank inside this chunk's share of the bucket (the returning
+  // atomic): k_partition places the draw from that word alone -- no second evaluation of the bucket function,
+  // no second counting pass.  Explicit groups: BHIST_UNROLL loads, then their bucket functions, then their
+  // atomics, then the stores, so that several draws' memory round trips overlap per thread (the compiler does
+  // not hoist loads across predicated blocks with shared-memory atomics).
 #pragma unroll 1
   for (int it0 = 0; it0 < PART_IPT; it0 += BHIST_UNROLL) {
     double v[BHIST_UNROLL];
@@ -280,23 +275,6 @@ __global__ void __launch_bounds__(PART_NT, B200REF_BHIST_OCC) k_bhist(const doub
       }
     }
   }
-#else
-#pragma unroll BHIST_UNROLL
-  for (int it = 0; it < PART_IPT; ++it) {
-    const uint32_t e = base + it * PART_NT + threadIdx.x;
-    if (e < M) {
-      const double v = xp[e];
-      bad |= !is_finite_bits(v);
-      const double d = v - c0;
-      s1 += d;
-      s2 = fma(d, d, s2);
-      // bucket and arrival rank inside this chunk's share of the bucket: k_partition places the draw
-      // from this word alone (no second evaluation of the bucket function, no second counting pass)
-      const uint32_t c = (uint32_t)coarse_of(v, lo, cs, sp, lut);
-      meta[e] = (c << 16) | atomicAdd(&cnt[c], 1u);
-    }
-  }
-#endif
   // deterministic block sums (fixed tree)
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -603,15 +581,11 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
   const uint64_t* pk = b.pkey + (size_t)p * M + B0;
   const uint32_t* pi = b.pidx + (size_t)p * M + B0;
   if constexpr (!TWO_PASS) {
-#if !(B200REF_FIN_LOAD2 && B200REF_FIN_RELOAD_IDX == 2)
-    double v[IPT];
-#endif
-    uint32_t fr[IPT];  // fine bucket | arrival rank in it << 16 (both below 2^16)
-#if !B200REF_FIN_RELOAD_IDX
-    uint32_t idx[IPT];
-#endif
-#if B200REF_FIN_LOAD2 && B200REF_FIN_RELOAD_IDX == 2
-    // keys in groups of FIN_LB: all loads of a group are in flight before the first bucket function needs its key
+    // Only the packed word (fine bucket | arrival rank in it << 16, both below 2^16) of every draw stays in
+    // registers across the scan; key and position are read again afterwards (L1 / L2 hits).  Holding them too
+    // spilled 3 words per draw at the 40 registers that 6 CTAs / SM allow (1.94 vs 1.70 ms on config 2).
+    uint32_t fr[IPT];
+    // keys in groups of LB: all loads of a group are in flight before the first bucket function needs its key
     constexpr int LB = (IPT % B200REF_FIN_LOAD2 == 0) ? B200REF_FIN_LOAD2 : 1;
 #pragma unroll
     for (int it = 0; it < IPT; it += LB) {
@@ -627,26 +601,9 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
         }
       }
     }
-#else
-#pragma unroll
-    for (int it = 0; it < IPT; ++it) {
-      if ((uint32_t)(it * NT) >= n) break;  // uniform: typical buckets fill 2-4 of the IPT slots
-      const uint32_t e = it * NT + tid;
-      if (e < n) {
-        v[it] = key2dbl(pk[e]);
-#if !B200REF_FIN_RELOAD_IDX
-        idx[it] = pi[e];
-#endif
-        const uint32_t f = (uint32_t)fine(v[it]);
-        fr[it] = f | (atomicAdd(&sm.fh[f], 1u) << 16);
-      }
-    }
-#endif
     __syncthreads();
     fine_scan<NT, NF, CAP>(sm);
     __syncthreads();
-#if B200REF_FIN_LOAD2 && B200REF_FIN_RELOAD_IDX == 2
-    // keys and positions are read again (L1 / L2 hits), in the same groups, and go to their slots
 #pragma unroll
     for (int it = 0; it < IPT; it += LB) {
       if ((uint32_t)(it * NT) >= n) break;
@@ -667,26 +624,6 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
         }
       }
     }
-#else
-#pragma unroll
-    for (int it = 0; it < IPT; ++it) {
-      if ((uint32_t)(it * NT) >= n) break;
-      const uint32_t e = it * NT + tid;
-      if (e < n) {
-        const uint32_t slot = sm.foff[fr[it] & 0xffffu] + (fr[it] >> 16);
-#if B200REF_FIN_RELOAD_IDX == 2
-        sm.kd[slot] = key2dbl(pk[e]);
-#else
-        sm.kd[slot] = v[it];
-#endif
-#if B200REF_FIN_RELOAD_IDX
-        sm.i2[slot] = pi[e];  // read after the scan (the line is in L1 / L2): one register less per draw across it
-#else
-        sm.i2[slot] = idx[it];
-#endif
-      }
-    }
-#endif
   } else {
     for (uint32_t e = tid; e < n; e += NT) atomicAdd(&sm.fh[fine(key2dbl(pk[e]))], 1u);
     __syncthreads();
@@ -984,9 +921,6 @@ using FinSmemBig = FinSmem<CAPBIG, NFINE_BIG>;
 #ifndef B200REF_FIN_OCC
 #define B200REF_FIN_OCC 6
 #endif
-#ifndef B200REF_FIN_DUAL
-#define B200REF_FIN_DUAL 0
-#endif
 #ifndef B200REF_FIN_BPC
 #define B200REF_FIN_BPC 8
 #endif
@@ -1044,13 +978,6 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
     }
 #endif
     if (n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
-      // buckets of up to half the capacity (almost all of them when M / 256 <= ~700) keep their draws in
-      // registers across the scan without spilling; the full-capacity instantiation spills 3 words per draw
-#if B200REF_FIN_DUAL
-      if (n <= (uint32_t)(FIN_NT * FIN_IPT / 2))
-        finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT / 2, false>(sm, ff, B0, n, M, p, b, fo);
-      else
-#endif
         finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, ff, B0, n, M, p, b, fo);
       __syncthreads();
     }

@@ -249,9 +249,6 @@ struct FoldOut {
 constexpr int FOLD_PAD_SH = B200REF_FOLD_PAD_SH;
 __device__ __forceinline__ uint32_t sdi(uint32_t i) { return i + (i >> FOLD_PAD_SH); }
 
-#ifndef B200REF_FOLD_ST
-#define B200REF_FOLD_ST 2
-#endif
 #ifndef B200REF_FOLD_OCC
 #define B200REF_FOLD_OCC 8
 #endif
@@ -428,15 +425,7 @@ __global__ void __launch_bounds__(RANK_NT, B200REF_FOLD_OCC) k_fold(RankBufs b, 
         zf = b.ztab[kk];
       }
       if (o.zz) {
-#if B200REF_FOLD_ST == 1
-        __stcg(&o.zz[pbase + pi[it]], make_double2(zb[it], zf));
-#elif B200REF_FOLD_ST == 2
-        __stcs(&o.zz[pbase + pi[it]], make_double2(zb[it], zf));
-#elif B200REF_FOLD_ST == 3
-        __stwt(&o.zz[pbase + pi[it]], make_double2(zb[it], zf));
-#else
-        o.zz[pbase + pi[it]] = make_double2(zb[it], zf);
-#endif
+        __stcs(&o.zz[pbase + pi[it]], make_double2(zb[it], zf));  // streaming store (.cs): -1.5 % against the default policy
       } else {
         if (o.z) o.z[pbase + pi[it]] = zb[it];
         if (o.zf) o.zf[pbase + pi[it]] = zf;

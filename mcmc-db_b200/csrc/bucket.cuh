@@ -464,6 +464,10 @@ __global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const d
 // ---------------------------------------------------------------- k_finish / k_finish_big
 struct FinishOut {
   double* rank;   // optional [PB][M]: average ranks scattered to original positions (ranks API)
+  // Statistics-only passes (mean / std / quantiles, no scores): the sorted positions the quantile step will
+  // read; k_finish then ranks only the buckets that hold one of them.  npos == 0: every bucket is ranked.
+  uint32_t pos[2 * 8 + 2];
+  int npos;
 };
 
 // Shared-memory layout of one finishing CTA (dynamic).
@@ -977,7 +981,14 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
       if (lane == 1 && c1 > 0) prefetch_line(&fn->sp[c1 - 1]);
     }
 #endif
-    if (n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
+    bool wanted = true;
+    if (fo.npos) {  // uniform: statistics-only pass
+      wanted = false;
+#pragma unroll
+      for (int i = 0; i < 2 * 8 + 2; ++i)  // static indices: the parameter struct stays in the constant bank
+        wanted |= (i < fo.npos) && (fo.pos[i] - B0 < n);  // unsigned: B0 <= pos < B0 + n
+    }
+    if (wanted && n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
         finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, ff, B0, n, M, p, b, fo);
       __syncthreads();
     }

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -437,8 +438,24 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
       LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
     else
       LAUNCH(K_PARTITION, st, k_partition_w<<<gc, PART_NT, sizeof(WideSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
-    LAUNCH(K_FINISH, st, k_finish<<<dim3((nb1 * nsub + FIN_BPC - 1) / FIN_BPC, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, nsub, nb1 * nsub, bb, FinishOut{rank_b_batch}));
-    LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, FinishOut{rank_b_batch}));
+    FinishOut fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.rank = rank_b_batch;
+    if (!want_scores && !rank_b) {
+      // statistics only: the order statistics k_param_prep reads (quantile_lerp's lo / hi, the median's one or two)
+      auto want = [&](int64_t t) { fin.pos[fin.npos++] = (uint32_t)std::min<int64_t>(std::max<int64_t>(t, 0), M - 1); };
+      want((M - 1) / 2);
+      want(M / 2);
+      for (int i = 0; i < nq; ++i) {
+        const double vi = (double)(M - 1) * q_host[i];
+        const int64_t lo = (int64_t)std::floor(vi);
+        want(lo);
+        want(lo + 1);
+      }
+    }
+    LAUNCH(K_FINISH, st, k_finish<<<dim3((nb1 * nsub + FIN_BPC - 1) / FIN_BPC, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, nsub, nb1 * nsub, bb, fin));
+    fin.npos = 0;  // oversize buckets are always ranked
+    LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, fin));
     CUDA_TRY(cudaStreamWaitEvent(st, side_stream(slot).join, 0));
 
     PrepOut po;

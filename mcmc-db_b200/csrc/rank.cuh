@@ -21,7 +21,10 @@
 
 namespace b200ref {
 
-constexpr int RANK_NT = 128;
+#ifndef B200REF_RANK_NT
+#define B200REF_RANK_NT 128
+#endif
+constexpr int RANK_NT = B200REF_RANK_NT;
 constexpr int RANK_IPT = 8;
 constexpr int RANK_TILE = RANK_NT * RANK_IPT;
 

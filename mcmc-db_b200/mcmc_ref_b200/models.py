@@ -131,6 +131,9 @@ MODELS: dict[str, GlmModel] = {
     "bangladesh_contraceptive-noncentered": GlmModel("bernoulli_logit", "use",
                                                      ("@onehot(district, D)", "@onehot(district, D) * urban[:, None]"),
                                                      ("a[*]", "b[*]"), source="bangladesh_contraceptive-noncentered.stan:17-31"),
+    # ---- autoregression: y[t] ~ normal(alpha + sum_k beta[k] * y[t - k], sigma), t = K + 1 .. T ----
+    "arK-arK": GlmModel("normal", "y[int(K):]", ("1", "@lagged(y, K)"), ("alpha", "beta[*]"), sigma="sigma",
+                        source="arK-arK.stan:11-26"),
     # ---- non-Gaussian GLMs ----
     "wells_data-wells_dist": GlmModel("bernoulli_logit", "switched", ("1", "dist"), _beta(2),
                                       source="wells_data-wells_dist.stan:9-11"),
@@ -154,6 +157,9 @@ def _env(data: Mapping[str, object]) -> dict[str, object]:
         "sd": lambda v: float(np.std(v, ddof=1)),          # Stan's sd() is the sample standard deviation
         "center": lambda m: m - np.mean(m, axis=0),        # brms' Xc
         "diag": np.diag,
+        "int": int,
+        # column k (1-based) = y[t - k] for t = K + 1 .. T
+        "lagged": lambda y, k: np.stack([y[int(k) - j:len(y) - j] for j in range(1, int(k) + 1)], axis=1),
         "onehot": lambda idx, k: (np.asarray(idx, dtype=np.int64)[:, None] == np.arange(1, int(k) + 1)[None, :]).astype(np.float64),
     }
     for key, value in data.items():

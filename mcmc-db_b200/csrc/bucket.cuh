@@ -898,9 +898,19 @@ __global__ void __launch_bounds__(PART_NT) k_partition_w(const double* __restric
   __syncthreads();
   // reserve this chunk's run in every bucket it touches: one global atomic per (chunk, bucket)
   uint32_t* cur = b.cur + (size_t)p * NBW_MAX;
-  for (int i = tid; i < nbt; i += PART_NT) {
-    const uint32_t c = sm.cnt[i];
-    if (c) sm.cnt[i] = atomicAdd(&cur[i], c);
+  // (groups of 8 returning atomics in flight per thread: one at a time, their round trips were the kernel)
+  for (int i0 = tid; i0 < nbt; i0 += 8 * PART_NT) {
+    uint32_t c[8], r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j * PART_NT;
+      c[j] = (i < nbt) ? sm.cnt[i] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = c[j] ? atomicAdd(&cur[i0 + j * PART_NT], c[j]) : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c[j]) sm.cnt[i0 + j * PART_NT] = r[j];
   }
   __syncthreads();
   uint64_t* ok = b.pkey + (size_t)p * M;

@@ -112,10 +112,23 @@ SideStream& side_stream(int slot = 0) {
 constexpr size_t ALIGN = 256;
 inline size_t up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 
+// Long chains: when a parameter's zz row (16 B per draw) is far beyond what L2 can merge into full sectors, the
+// score scatter goes through at most 32 destination windows of >= 2^20 positions (16 MB of zz; 2^19 / 2^20 / 2^21 measured
+// 14.7 / 14.5 / 15.7 ms for k_fold + k_unbin on config 4, direct scatter 17.9 ms); 0 = direct scatter.
+#ifndef B200REF_BIN_MIN_SHIFT
+#define B200REF_BIN_MIN_SHIFT 20
+#endif
+inline int fold_bin_shift(int64_t M) {
+  if (M <= ((int64_t)3 << 20)) return 0;
+  int lg = 0;
+  while (((int64_t)1 << lg) < M) ++lg;
+  return std::max(B200REF_BIN_MIN_SHIFT, lg - 5);
+}
+
 // Workspace carve-up for one batch of PB parameters with M pooled draws each.
 struct Layout {
   size_t ztab, zodd, flag, header;  // shared part
-  size_t pkey, skey, pidx, sidx, kcode, zz, fn, cnt, boff, cur, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
+  size_t pkey, skey, pidx, sidx, kcode, zz, rzf, bcur, fn, cnt, boff, cur, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
       crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cgpend, cgprev, cwl0, cwl1, cnwl, per_batch;
   uint32_t ntiles, nchunks;
   void compute(int64_t PB, int64_t M, bool diag, int64_t C = 1, int64_t N = 1) {
@@ -134,6 +147,9 @@ struct Layout {
     sidx = b; b += up(n * 4);
     kcode = b; b += up(n * 4);
     zz = b; b += diag ? up(n * 16) : 0;
+    const bool binned = diag && fold_bin_shift(M) != 0;  // long chains: record segments for the two-step scatter
+    rzf = b; b += binned ? up(n * 8) : 0;
+    bcur = b; b += binned ? up((size_t)PB * 32 * 4) : 0;
     fn = b; b += up((size_t)PB * sizeof(BucketFn));
     const bool wide = choose_sub(M) > 1;  // long chains: sub-bucketed coarse buckets, no per-chunk counts
     cnt = b; b += wide ? 0 : up((size_t)PB * nchunks * NB1_MAX * 4);
@@ -468,11 +484,25 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     if (want_scores) {
       LAUNCH(K_MPART, st, k_merge_partition<<<dim3((L.ntiles + 1 + 127) / 128, PB), 128, 0, st>>>(rb, (uint32_t)M, L.ntiles, PB));
       FoldOut fo;
+      memset(&fo, 0, sizeof(fo));
       fo.zz = zz;
       fo.z = z_b ? z_b + (size_t)p0 * M : nullptr;
       fo.zf = z_f ? z_f + (size_t)p0 * M : nullptr;
       fo.rankf = rank_f ? rank_f + (size_t)p0 * M : nullptr;
+      fo.bin_shift = (zz && !fo.z && !fo.zf && !fo.rankf) ? fold_bin_shift(M) : 0;
+      if (fo.bin_shift) {
+        // record segments live in buffers that are dead by now (the partitioned keys / positions) + one more plane
+        fo.cursor = (uint32_t*)(wb + L.bcur);
+        fo.rpos = bb.pidx;
+        fo.rzb = (double*)bb.pkey;
+        fo.rzf = (double*)(wb + L.rzf);
+        CUDA_TRY(cudaMemsetAsync(fo.cursor, 0, (size_t)PB * 32 * 4, st));
+      }
       LAUNCH(K_FOLD, st, k_fold<<<gt, RANK_NT, 0, st>>>(rb, (uint32_t)M, L.ntiles, fo));
+      if (fo.bin_shift) {
+        const unsigned gx = (unsigned)((M + UNBIN_NT * UNBIN_IPT - 1) / (UNBIN_NT * UNBIN_IPT));
+        LAUNCH(K_FOLD, st, k_unbin<<<dim3(gx, PB), UNBIN_NT, 0, st>>>(fo, bb.fallback, flag, (uint32_t)M));
+      }
     }
     ChainState cs;
     memset(&cs, 0, sizeof(cs));

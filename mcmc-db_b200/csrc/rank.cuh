@@ -241,6 +241,13 @@ struct FoldOut {
   double* z;           // separate outputs (ranks API), any may be null
   double* zf;
   double* rankf;
+  // Long chains (a parameter's zz row does not fit L2): the scatter goes through per-destination-window record
+  // segments (k_fold appends {position, z_bulk, z_folded}, k_unbin scatters window by window).  bin_shift = 0: direct.
+  int bin_shift;       // window = positions >> bin_shift (at most 32 windows per parameter)
+  uint32_t* cursor;    // [PB][32] records appended to each window's segment so far
+  uint32_t* rpos;      // [PB][M] records: original position   (segment of window r starts at r << bin_shift)
+  double* rzb;         // [PB][M]          z_bulk
+  double* rzf;         // [PB][M]          z_folded
 };
 
 // Index into the folded-bits window: one pad word per 16 keeps the merge's reads (neighbouring threads
@@ -407,26 +414,67 @@ __global__ void __launch_bounds__(RANK_NT, B200REF_FOLD_OCC) k_fold(RankBufs b, 
   // per window slot (the order the loads came in): folded score of the slot's merged position, then
   // the only random access, the 16-byte scatter
   const size_t pbase = (size_t)p * M;
+  // folded score (and code) of window slot w
+  auto fold_score = [&](uint32_t w, uint32_t& kk, double& zf) {
+    if (!any_tie) {
+      const uint32_t e = dest[w];
+      kk = 2u * (gbase + e) + 1u;
+      zf = szf[e];
+    } else {
+      // tie run [i, j) of this slot's folded value in the whole folded order
+      const uint64_t d = sd[sdi(w)];
+      const uint32_t il = window_bound<false>(sd, 0, nl, d) + (window_bound<false>(sd, nl, nl + nr, d) - nl);
+      const uint32_t jl = window_bound<true>(sd, 0, nl, d) + (window_bound<true>(sd, nl, nl + nr, d) - nl);
+      const uint32_t i = (il == 0) ? ext[0] : gbase + il;
+      const uint32_t j = (jl == n) ? ext[1] : gbase + jl;
+      kk = i + j;
+      zf = b.ztab[kk];
+    }
+  };
+  if (o.bin_shift && o.zz && !b.fallback[p]) {
+    // Long chains: a 16-byte store into a 128 MB row is a DRAM read-modify-write of its own (13 of config 4's
+    // 18 ms in this kernel).  The tile's records are appended to the segment of their destination window
+    // instead -- every window receives exactly as many records as it has positions, so segment r starts at
+    // r << bin_shift -- in runs reserved with one global atomic per (tile, window); k_unbin then scatters one
+    // window's segment at a time, inside what L2 can merge into full sectors.
+    __shared__ uint32_t bcnt[32], bbase[32];
+    if (tid < 32) bcnt[tid] = 0;
+    __syncthreads();
+    uint32_t rr[RANK_IPT];  // window | arrival rank in the tile's share of it << 5
+#pragma unroll
+    for (int it = 0; it < RANK_IPT; ++it) {
+      const uint32_t w = it * RANK_NT + tid;
+      if (w < n) {
+        const uint32_t r = pi[it] >> o.bin_shift;
+        rr[it] = r | (atomicAdd(&bcnt[r], 1u) << 5);
+      }
+    }
+    __syncthreads();
+    if (tid < 32 && bcnt[tid]) bbase[tid] = atomicAdd(&o.cursor[(size_t)p * 32 + tid], bcnt[tid]);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < RANK_IPT; ++it) {
+      const uint32_t w = it * RANK_NT + tid;
+      if (w < n) {
+        uint32_t kk;
+        double zf;
+        fold_score(w, kk, zf);
+        const uint32_t r = rr[it] & 31u;
+        const size_t slot = pbase + ((size_t)r << o.bin_shift) + bbase[r] + (rr[it] >> 5);
+        o.rpos[slot] = pi[it];
+        o.rzb[slot] = zb[it];
+        o.rzf[slot] = zf;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int it = 0; it < RANK_IPT; ++it) {
     const uint32_t w = it * RANK_NT + tid;
     if (w < n) {
       uint32_t kk;
       double zf;
-      if (!any_tie) {
-        const uint32_t e = dest[w];
-        kk = 2u * (gbase + e) + 1u;
-        zf = szf[e];
-      } else {
-        // tie run [i, j) of this slot's folded value in the whole folded order
-        const uint64_t d = sd[sdi(w)];
-        const uint32_t il = window_bound<false>(sd, 0, nl, d) + (window_bound<false>(sd, nl, nl + nr, d) - nl);
-        const uint32_t jl = window_bound<true>(sd, 0, nl, d) + (window_bound<true>(sd, nl, nl + nr, d) - nl);
-        const uint32_t i = (il == 0) ? ext[0] : gbase + il;
-        const uint32_t j = (jl == n) ? ext[1] : gbase + jl;
-        kk = i + j;
-        zf = b.ztab[kk];
-      }
+      fold_score(w, kk, zf);
       if (o.zz) {
         __stcs(&o.zz[pbase + pi[it]], make_double2(zb[it], zf));  // streaming store (.cs): -1.5 % against the default policy
       } else {
@@ -436,6 +484,29 @@ __global__ void __launch_bounds__(RANK_NT, B200REF_FOLD_OCC) k_fold(RankBufs b, 
       }
     }
   }
+}
+
+// Second half of the long-chain scatter: record s of a parameter (segments in window order) goes to its
+// position.  Consecutive CTAs walk consecutive records, i.e. one destination window at a time.
+constexpr int UNBIN_NT = 256, UNBIN_IPT = 8;
+__global__ void __launch_bounds__(UNBIN_NT) k_unbin(FoldOut o, const uint8_t* __restrict__ fallback, const int* __restrict__ flag,
+                                                    uint32_t M) {
+  const int p = blockIdx.y;
+  if ((*flag & 1) || fallback[p]) return;
+  const size_t pbase = (size_t)p * M;
+  const uint32_t s0 = blockIdx.x * (UNBIN_NT * UNBIN_IPT) + threadIdx.x;
+  uint32_t pos[UNBIN_IPT];
+  double zb[UNBIN_IPT], zf[UNBIN_IPT];
+#pragma unroll
+  for (int j = 0; j < UNBIN_IPT; ++j) {
+    const uint32_t s = min(s0 + j * UNBIN_NT, M - 1);
+    pos[j] = o.rpos[pbase + s];
+    zb[j] = o.rzb[pbase + s];
+    zf[j] = o.rzf[pbase + s];
+  }
+#pragma unroll
+  for (int j = 0; j < UNBIN_IPT; ++j)
+    if (s0 + j * UNBIN_NT < M) __stcs(&o.zz[pbase + pos[j]], make_double2(zb[j], zf[j]));
 }
 
 }  // namespace b200ref

@@ -552,6 +552,13 @@ __device__ __forceinline__ void warp_sort_pairs(double* __restrict__ kd, uint32_
 // Monotone in x (one subtraction, one fused multiply-add, A >= 0), which is all exactness needs.
 struct FineFn {
   double L, A, B;
+  // k_finish_big only: the two outermost buckets of a parameter also hold every draw beyond the sample's
+  // extremes (~M / 4096 of them, far more for heavy tails).  Clamped, they would all share the first / last
+  // fine bucket and be sorted by a single warp (2.9 ms of config 4's step).  edge: 0 none, 1 the bucket below
+  // which there is nothing (x0 = sample minimum), 2 the bucket above which there is nothing (x0 = sample
+  // maximum); w = 1 / (bucket width).
+  int edge;
+  double x0, w;
 };
 
 template <int NF>
@@ -562,11 +569,35 @@ __device__ __forceinline__ FineFn make_fine(const BucketFn* fn, int cb, int nsub
   f.L = (c == 0) ? fn->lo : fn->sp[c - 1];
   f.A = fn->fsub[c] * (double)NF;
   f.B = -(double)((cb - (c << sh)) * NF);  // 0 when the coarse buckets are the buckets (nsub == 1)
+  f.edge = 0;
+  f.x0 = 0.0;
+  f.w = fn->fsub[c];
+  const int nb1 = fn->nb1;
+  if (cb == 0) { f.edge = 1; f.x0 = fn->lo; }
+  else if (cb == nb1 * nsub - 1) { f.edge = 2; f.x0 = fn->hi; }
   return f;
 }
 
+// Edge buckets (k_finish_big): the bucket's own range takes half of the fine buckets, the draws beyond the
+// sample's extreme the other half, spread by the logarithm of their distance in bucket widths (64 fine buckets
+// per doubling at NF = 2048).  Monotone in x on both pieces and across x0.
 template <int NF>
+__device__ __forceinline__ int fine_edge(const FineFn& ff, double x) {
+  constexpr double SPREAD = (double)(NF / 2) / 16.0;
+  const int inner = min(max(__double2int_rd(fma(x - ff.L, ff.A, ff.B) * 0.5), 0), NF / 2 - 1);
+  if (ff.edge == 1) {
+    if (x >= ff.x0) return NF / 2 + inner;
+    const int far = min(__double2int_rd(log2(1.0 + (ff.x0 - x) * ff.w) * SPREAD), NF / 2 - 1);
+    return NF / 2 - 1 - max(far, 0);
+  }
+  if (x <= ff.x0) return inner;
+  const int far = min(__double2int_rd(log2(1.0 + (x - ff.x0) * ff.w) * SPREAD), NF / 2 - 1);
+  return NF / 2 + max(far, 0);
+}
+
+template <int NF, bool EDGE>
 __device__ __forceinline__ int fine_bucket(const FineFn& ff, double x) {
+  if (EDGE && ff.edge) return fine_edge<NF>(ff, x);  // uniform per bucket
   // cvt.rmi.s32.f64 saturates (NaN -> 0), the integer clamp finishes the job
   return min(max(__double2int_rd(fma(x - ff.L, ff.A, ff.B)), 0), NF - 1);
 }
@@ -574,11 +605,11 @@ __device__ __forceinline__ int fine_bucket(const FineFn& ff, double x) {
 // Rank every draw of one bucket (n draws, sorted offset B0) exactly.
 // TWO_PASS = false: the bucket is read once into registers (n <= NT * IPT);
 // TWO_PASS = true : any n <= CAP, the bucket is read twice and slots come from cursors.
-template <int NT, int NF, int CAP, int IPT, bool TWO_PASS>
+template <int NT, int NF, int CAP, int IPT, bool TWO_PASS, bool EDGE>
 __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn ff, uint32_t B0, uint32_t n,
                                               uint32_t M, int p, const BucketBufs& b, const FinishOut& fo) {
   const int tid = threadIdx.x;
-  auto fine = [&](double x) -> int { return fine_bucket<NF>(ff, x); };
+  auto fine = [&](double x) -> int { return fine_bucket<NF, EDGE>(ff, x); };
   for (int i = tid; i < NF; i += NT) sm.fh[i] = 0;
   if (tid == 0) sm.nbig = 0;
   __syncthreads();
@@ -999,7 +1030,7 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
         wanted |= (i < fo.npos) && (fo.pos[i] - B0 < n);  // unsigned: B0 <= pos < B0 + n
     }
     if (wanted && n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
-        finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false>(sm, ff, B0, n, M, p, b, fo);
+        finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false, false>(sm, ff, B0, n, M, p, b, fo);
       __syncthreads();
     }
   }
@@ -1018,7 +1049,7 @@ __global__ void __launch_bounds__(FINB_NT) k_finish_big(uint32_t M, BucketBufs b
     const uint32_t B0 = b.boff[(size_t)p * b.bstride + cb];
     const uint32_t n = b.boff[(size_t)p * b.bstride + cb + 1] - B0;
     __syncthreads();
-    finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true>(sm, make_fine<NFINE_BIG>(b.fn + p, cb, nsub), B0, n, M, p, b, fo);
+    finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true, true>(sm, make_fine<NFINE_BIG>(b.fn + p, cb, nsub), B0, n, M, p, b, fo);
   }
 }
 

@@ -1041,7 +1041,9 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
 __global__ void __launch_bounds__(FINB_NT) k_finish_big(uint32_t M, BucketBufs b, FinishOut fo) {
   extern __shared__ __align__(16) unsigned char fin_smem_raw[];
   FinSmemBig& sm = *reinterpret_cast<FinSmemBig*>(fin_smem_raw);
-  const int nbig = *b.nbigb;
+  // k_bscan / k_bscan_w keep counting past the end of the list (and send those parameters to the LSD
+  // fallback): only the entries that were actually stored may be read
+  const int nbig = min(*b.nbigb, b.biglist_cap);
   const int nsub = choose_sub(M);
   for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
     const int p = b.biglist[2 * q], cb = b.biglist[2 * q + 1];

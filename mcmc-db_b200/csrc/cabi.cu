@@ -62,8 +62,10 @@ std::mutex g_prof_mu;
 double g_prof_ms[K_COUNT];
 uint64_t g_prof_n[K_COUNT];
 
-inline void prof_begin(int id, cudaStream_t st) {
-  if (!g_prof) return;
+// returns the index of the record this launch owns (-1: profiling off), so that two host threads
+// launching at once each close their own record
+inline long prof_begin(int id, cudaStream_t st) {
+  if (!g_prof) return -1;
   ProfRec r;
   r.id = id;
   cudaEventCreate(&r.a);
@@ -71,18 +73,19 @@ inline void prof_begin(int id, cudaStream_t st) {
   cudaEventRecord(r.a, st);
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_recs.push_back(r);
+  return (long)g_prof_recs.size() - 1;
 }
-inline void prof_end(cudaStream_t st) {
-  if (!g_prof) return;
+inline void prof_end(long rec, cudaStream_t st) {
+  if (rec < 0) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  cudaEventRecord(g_prof_recs.back().b, st);
+  if ((size_t)rec < g_prof_recs.size()) cudaEventRecord(g_prof_recs[(size_t)rec].b, st);
 }
 
 #define LAUNCH(id, st, ...)                                 \
   do {                                                      \
-    prof_begin((id), (st));                                 \
+    const long prof_rec_ = prof_begin((id), (st));          \
     __VA_ARGS__;                                            \
-    prof_end((st));                                         \
+    prof_end(prof_rec_, (st));                              \
     g_launches.fetch_add(1, std::memory_order_relaxed);     \
   } while (0)
 
@@ -129,7 +132,7 @@ inline int fold_bin_shift(int64_t M) {
 struct Layout {
   size_t ztab, zodd, flag, header;  // shared part
   size_t pkey, skey, pidx, sidx, kcode, zz, rzf, bcur, fn, cnt, boff, cur, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
-      crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cgpend, cgprev, cwl0, cwl1, cnwl, per_batch;
+      crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cgpend, cgprev, cwl0, cwl1, cnwl, cgbar, per_batch;
   uint32_t ntiles, nchunks;
   void compute(int64_t PB, int64_t M, bool diag, int64_t C = 1, int64_t N = 1) {
     ntiles = (uint32_t)((M + RANK_TILE - 1) / RANK_TILE);
@@ -188,6 +191,7 @@ struct Layout {
       cwl0 = b; b += up((size_t)2 * PB * 4);
       cwl1 = b; b += up((size_t)2 * PB * 4);
       cnwl = b; b += up(2 * sizeof(int));
+      cgbar = b; b += up(sizeof(unsigned int));
     }
     per_batch = b;
   }
@@ -206,7 +210,22 @@ int64_t fit_batch(int64_t P, int64_t M, bool diag, size_t ws_bytes, int64_t cap,
 }
 
 constexpr int64_t BATCH_CAP = 4096;
+constexpr int MAX_CHAINS = 4096;  // k_decide0 keeps 3 doubles per chain in shared memory
 constexpr int FALLBACK_GRID = 296;  // CTAs striding over the fallback list (2 per SM)
+
+// CTAs of the persistent rounds kernel: as many as are resident at once (cooperative launch), per device.
+int rounds_grid() {
+  static int grid_dev[MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (grid_dev[dev] == 0) {
+    int per_sm = 0, nsm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ess_rounds, MO_CTA, sizeof(RoundsSmem)) != cudaSuccess ||
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return -1;
+    grid_dev[dev] = per_sm * nsm > 0 ? per_sm * nsm : -1;
+  }
+  return grid_dev[dev];
+}
 
 // ---- small kernels used only by the orchestration ----
 
@@ -334,7 +353,11 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   if (nq < 0 || nq > B200REF_MAX_QUANTILES) return fail(B200REF_ERR_ARG, "nq=%d out of range", nq);
   if (P == 0) return B200REF_OK;
   if (!ws) return fail(B200REF_ERR_WORKSPACE, "null workspace");
-  if (mode.diag && C > 4096) return fail(B200REF_ERR_ARG, "more than 4096 chains are not supported (C=%lld)", (long long)C);
+  if (mode.diag && C > MAX_CHAINS) return fail(B200REF_ERR_ARG, "more than %d chains are not supported (C=%lld)", MAX_CHAINS, (long long)C);
+  // numpy.quantile raises for levels outside [0, 1] (backends_numpy.py:44); NaN fails both comparisons
+  for (int i = 0; i < nq; ++i)
+    if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0))
+      return fail(B200REF_ERR_ARG, "quantile level %g is outside [0, 1]", q_host[i]);
   const bool need_z = mode.diag;
   const bool ws_zz = mode.diag;  // interleaved {z_bulk, z_folded} scratch for k_chain
   const int64_t PBmax = fit_batch(P, M, ws_zz, ws_bytes, BATCH_CAP, C, N);
@@ -346,16 +369,25 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   double* zodd = (double*)(w + L.zodd);
   int* flag = (int*)(w + L.flag);
   char* wb = w + L.header;
-  static bool part_attr_dev[MAX_DEVICES] = {};  // function attributes are per device
-  bool& part_attr = part_attr_dev[current_device()];
-  if (!part_attr) {
-    CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
-    CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemSmall)));
-    CUDA_TRY(cudaFuncSetAttribute(k_finish_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinSmemBig)));
-    CUDA_TRY(cudaFuncSetAttribute(k_moments0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Mo0Smem)));
-    CUDA_TRY(cudaFuncSetAttribute(k_moments_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoRSmem)));
-    CUDA_TRY(cudaFuncSetAttribute(k_moments_r1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoR1Smem)));
-    part_attr = true;
+  {
+    // function attributes are per device; several host threads may arrive here at once
+    static std::once_flag attr_once[MAX_DEVICES];
+    static cudaError_t attr_err[MAX_DEVICES];
+    const int dev = current_device();
+    std::call_once(attr_once[dev], [dev] {
+      cudaError_t e = cudaSuccess;
+      auto set = [&e](const void* f, size_t bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      };
+      set((const void*)k_partition, sizeof(PartSmem));
+      set((const void*)k_finish, sizeof(FinSmemSmall));
+      set((const void*)k_finish_big, sizeof(FinSmemBig));
+      set((const void*)k_moments0, sizeof(Mo0Smem));
+      set((const void*)k_ess_rounds, sizeof(RoundsSmem));
+      set((const void*)k_decide0, 3 * (size_t)MAX_CHAINS * sizeof(double));  // 96 KB at the advertised 4096 chains
+      attr_err[dev] = e;
+    });
+    CUDA_TRY(attr_err[dev]);
   }
 
   CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -534,19 +566,19 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
         LAUNCH(K_CHAIN, st, k_moments0<<<dim3(gx, PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, upc, cs.part));
       }
       LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
-      int cur = 0;
-      for (uint32_t t0 = 1 + LAGB; t0 < (uint32_t)N; t0 += LAGR) {
-        int nwork = 0;
-        CUDA_TRY(cudaMemcpyAsync(&nwork, cs.nwl + cur, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (nwork == 0) break;
-        CUDA_TRY(cudaMemsetAsync(cs.nwl + (cur ^ 1), 0, sizeof(int), st));
-        if (t0 <= (uint32_t)MO_T0MAX)
-          LAUNCH(K_CHAIN, st, k_moments_r1<<<dim3((unsigned)(C * g.nunits), nwork), MO_CTA, sizeof(MoR1Smem), st>>>(zz, g, t0, cs.wl[cur], cs.partr));
-        else
-          LAUNCH(K_CHAIN, st, k_moments_r<<<dim3((unsigned)(C * g.nunits), nwork), MO_CTA, sizeof(MoRSmem), st>>>(zz, g, t0, cs.wl[cur], cs.partr));
-        LAUNCH(K_DECIDE, st, k_decide_r<<<nwork, DEC_NT, 0, st>>>(zz, g, PB, t0, cur, cs));
-        cur ^= 1;
+      if ((uint32_t)N > 1u + LAGB) {
+        // every later round (32 lags each) in ONE cooperative launch: the grid loops on the device until the
+        // work list is empty -- no list length travels to the host, nothing synchronises between rounds
+        unsigned int* gbar = (unsigned int*)(wb + L.cgbar);
+        CUDA_TRY(cudaMemsetAsync(gbar, 0, sizeof(unsigned int), st));
+        const double2* zzc = zz;
+        ChainGeom gg = g;
+        int pbv = PB;
+        void* args[] = {(void*)&zzc, (void*)&gg, (void*)&pbv, (void*)&cs, (void*)&gbar};
+        const int grid = rounds_grid();
+        if (grid < 1) return fail(B200REF_ERR_CUDA, "k_ess_rounds cannot be made resident on this device");
+        LAUNCH(K_CHAIN, st, CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ess_rounds, dim3((unsigned)grid), dim3(MO_CTA), args,
+                                                                sizeof(RoundsSmem), st)));
       }
     }
     if (out) {

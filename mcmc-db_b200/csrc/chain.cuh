@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restric
 }
 
 // ---------------------------------------------------------------- later rounds: one kind, lags t0 .. t0+31
-// grid (C * nunits, nwork), 256 threads.  Two TMA-staged tiles per sub-tile: first factors y[i] and
+// One unit = (listed item, chain, unit of the chain), 256 threads.  Two TMA-staged tiles per sub-tile: first factors y[i] and
 // second factors y[i + t0 + ...]; threads 0-127 accumulate lags t0..t0+15, threads 128-255 lags
 // t0+16..t0+31 over the same draws, so one pass over a sticky chain advances 32 lags.
 struct MoRSmem {
@@ -296,44 +296,34 @@ struct MoRSmem {
   double ya[MO_PAD0];
   double yw[MO_PADR];
   double red[2][MO_NT / 32][LAGB];
-  uint64_t bar;
 };
 
-__global__ void __launch_bounds__(MO_CTA, 2) k_moments_r(const double2* __restrict__ zz, ChainGeom g, uint32_t t0,
-                                                         const int* __restrict__ wl, double* partr) {
-  extern __shared__ __align__(128) unsigned char mo_smem_raw[];
-  MoRSmem& S = *reinterpret_cast<MoRSmem*>(mo_smem_raw);
-  const int item = wl[blockIdx.y];
-  const int p = item >> 1, kind = item & 1;
-  const uint32_t c = blockIdx.x / g.nunits, u = blockIdx.x % g.nunits;
+// One work unit (one unit of one chain of one listed item) of a later round, two-tile variant.
+// `zc` = the chain's first pair, `out` = this unit's LAGR partial sums.  The CTA's mbarrier phase is carried
+// across units by the caller (persistent CTAs).
+__device__ __forceinline__ void moments_r_unit(MoRSmem& S, const double2* __restrict__ zc, const ChainGeom& g, uint32_t t0,
+                                               int kind, uint32_t u, double* __restrict__ out, uint64_t* bar, uint32_t& phase) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int hb = tid >> 7, ct = tid & (MO_NT - 1), wp = ct >> 5;  // hb: which block of 16 lags
   uint32_t a, b;
   unit_range(g, u, a, b);
   const uint32_t lim = (g.N > t0) ? g.N - t0 : 0;  // first factors need i + t0 < N
   b = min(b, lim);
-  const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
-  if (tid == 0) {
-    mbar_init(&S.bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
   auto stage = [&](uint32_t sub) {  // sub < lim, so both copies are non-empty
     fence_proxy_async();
     const uint32_t na = min((uint32_t)MO_RAW0, g.N - sub), nw = min((uint32_t)MO_RAWR, g.N - (sub + t0));
-    mbar_expect_tx(&S.bar, (na + nw) * 16u);
-    bulk_g2s(S.rawa, zc + sub, na * 16u, &S.bar);
-    bulk_g2s(S.raww, zc + sub + t0, nw * 16u, &S.bar);
+    mbar_expect_tx(bar, (na + nw) * 16u);
+    bulk_g2s(S.rawa, zc + sub, na * 16u, bar);
+    bulk_g2s(S.raww, zc + sub + t0, nw * 16u, bar);
   };
   double acc[LAGB];
 #pragma unroll
   for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
   if (a < b && tid == 0) stage(a);
-  uint32_t phase = 0;
   for (uint32_t sub = a; sub < b; sub += MO_SUB) {
     const uint32_t len = min((uint32_t)MO_SUB, b - sub);
     const uint32_t na = min((uint32_t)MO_RAW0, g.N - sub), nw = min((uint32_t)MO_RAWR, g.N - (sub + t0));
-    mbar_wait(&S.bar, phase);
+    mbar_wait(bar, phase);
     phase ^= 1u;
     {
       const double* ra = reinterpret_cast<const double*>(S.rawa) + kind;
@@ -374,8 +364,9 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments_r(const double2* __restri
     double v = S.red[hb][0][ct];
 #pragma unroll
     for (int k = 1; k < MO_NT / 32; ++k) v += S.red[hb][k][ct];
-    partr[(((size_t)blockIdx.y * g.C + c) * g.nunits + u) * LAGR + hb * LAGB + ct] = v;
+    out[hb * LAGB + ct] = v;
   }
+  __syncthreads();  // S.red and the staging buffers are free for the CTA's next unit
 }
 
 // ---------------------------------------------------------------- later rounds, near lags: ONE staged tile
@@ -391,40 +382,27 @@ struct MoR1Smem {
   double2 raw[MO_RAW1];
   double y[MO_PAD1];
   double red[2][MO_NT / 32][LAGB];
-  uint64_t bar;
 };
 
-__global__ void __launch_bounds__(MO_CTA, 2) k_moments_r1(const double2* __restrict__ zz, ChainGeom g, uint32_t t0,
-                                                          const int* __restrict__ wl, double* partr) {
-  extern __shared__ __align__(128) unsigned char mo_smem_raw[];
-  MoR1Smem& S = *reinterpret_cast<MoR1Smem*>(mo_smem_raw);
-  const int item = wl[blockIdx.y];
-  const int p = item >> 1, kind = item & 1;
-  const uint32_t c = blockIdx.x / g.nunits, u = blockIdx.x % g.nunits;
+__device__ __forceinline__ void moments_r1_unit(MoR1Smem& S, const double2* __restrict__ zc, const ChainGeom& g, uint32_t t0,
+                                                int kind, uint32_t u, double* __restrict__ out, uint64_t* bar, uint32_t& phase) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int hb = tid >> 7, ct = tid & (MO_NT - 1), wp = ct >> 5;  // hb: which block of 16 lags
   uint32_t a, b;
   unit_range(g, u, a, b);
   const uint32_t lim = (g.N > t0) ? g.N - t0 : 0;  // first factors need i + t0 < N
   b = min(b, lim);
-  const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
   const uint32_t span = MO_SUB + t0 + LAGR + CHUNK;  // pairs a full sub-tile touches
-  if (tid == 0) {
-    mbar_init(&S.bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
   double acc[LAGB];
 #pragma unroll
   for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
-  if (a < b && tid == 0) stage_pairs(S.raw, zc + a, min(span, g.N - a), &S.bar);
+  if (a < b && tid == 0) stage_pairs(S.raw, zc + a, min(span, g.N - a), bar);
   const uint32_t goff = (t0 - 1) / CHUNK + (uint32_t)hb;  // group offset of the second-factor window
-  uint32_t phase = 0;
   for (uint32_t sub = a; sub < b; sub += MO_SUB) {
     const uint32_t len = min((uint32_t)MO_SUB, b - sub);
     const uint32_t nel = min(span, g.N - sub);                       // pairs the copy delivered; the rest reads as 0
     const uint32_t need = min(span, len + t0 + LAGR + CHUNK);        // pairs this sub-tile's threads touch
-    mbar_wait(&S.bar, phase);
+    mbar_wait(bar, phase);
     phase ^= 1u;
     {
       const double* rk = reinterpret_cast<const double*>(S.raw) + kind;
@@ -444,7 +422,7 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments_r1(const double2* __restr
       }
     }
     __syncthreads();
-    if (tid == 0 && sub + MO_SUB < b) stage_pairs(S.raw, zc + sub + MO_SUB, min(span, g.N - (sub + MO_SUB)), &S.bar);
+    if (tid == 0 && sub + MO_SUB < b) stage_pairs(S.raw, zc + sub + MO_SUB, min(span, g.N - (sub + MO_SUB)), bar);
     const uint32_t i0 = ct * CHUNK;
     if (i0 < len) {
       const uint32_t nvalid = min((uint32_t)CHUNK, len - i0);
@@ -469,12 +447,14 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments_r1(const double2* __restr
     double v = S.red[hb][0][ct];
 #pragma unroll
     for (int k = 1; k < MO_NT / 32; ++k) v += S.red[hb][k][ct];
-    partr[(((size_t)blockIdx.y * g.C + c) * g.nunits + u) * LAGR + hb * LAGB + ct] = v;
+    out[hb * LAGB + ct] = v;
   }
+  __syncthreads();  // S.red and the staging buffer are free for the CTA's next unit
 }
 
 constexpr int DEC_RED = LAGR + 2;
-// block-wide sums of n values (n <= DEC_RED) over DEC_NT = 64 threads, fixed order; result in out[] (shared)
+// block-wide sums of n values (n <= DEC_RED) over NT threads, fixed order; result in out[] (shared)
+template <int NT>
 __device__ __forceinline__ void dec_reduce(double* vals, int n, double (*red)[DEC_RED], double* out) {
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   for (int k = 0; k < n; ++k) {
@@ -486,7 +466,7 @@ __device__ __forceinline__ void dec_reduce(double* vals, int n, double (*red)[DE
   __syncthreads();
   if (threadIdx.x < n) {
     double v = 0.0;
-    for (int k = 0; k < DEC_NT / 32; ++k) v += red[k][threadIdx.x];
+    for (int k = 0; k < NT / 32; ++k) v += red[k][threadIdx.x];
     out[threadIdx.x] = v;
   }
   __syncthreads();
@@ -604,7 +584,7 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
     st.head[(size_t)item * C + c] = hs;
     st.tail[(size_t)item * C + c] = ts;
   }
-  dec_reduce(vals, 2 + LAGB, red, tot);
+  dec_reduce<DEC_NT>(vals, 2 + LAGB, red, tot);
   if (threadIdx.x == 0) {
     const size_t o = (size_t)kind * PB + p;
     // ---- R-hat on the 2C split chains of length half ----
@@ -671,23 +651,25 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
 }
 
 // ---------------------------------------------------------------- later rounds: lags t0 .. t0+31 of the listed items
-__global__ void __launch_bounds__(DEC_NT) k_decide_r(const double2* __restrict__ zz, ChainGeom g, int PB, uint32_t t0,
-                                                     int cur, ChainState st) {
-  __shared__ double red[DEC_NT / 32][DEC_RED];
-  __shared__ double tot[DEC_RED];
-  const int item = st.wl[cur][blockIdx.x], p = item >> 1, kind = item & 1;
+// Decision for list entry `li` of the current list (NT threads of the CTA take part): sums the round's
+// partial lag products over chains and units, centres them, continues the rho walk.  Partial sums and
+// list entries were written by other CTAs of the same launch: read past L1 (ld.global.cg).
+template <int NT>
+__device__ __forceinline__ void decide_r_item(const double2* __restrict__ zz, const ChainGeom& g, int PB, uint32_t t0, int cur,
+                                              int li, const ChainState& st, double (*red)[DEC_RED], double* tot) {
+  const int item = __ldcg(&st.wl[cur][li]), p = item >> 1, kind = item & 1;
   const uint32_t C = g.C, N = g.N;
   double vals[LAGR];
   for (int k = 0; k < LAGR; ++k) vals[k] = 0.0;
-  for (uint32_t c = threadIdx.x; c < C; c += DEC_NT) {
-    const double* pc = st.partr + ((size_t)blockIdx.x * C + c) * g.nunits * LAGR;
+  for (uint32_t c = threadIdx.x; c < C; c += NT) {
+    const double* pc = st.partr + ((size_t)li * C + c) * g.nunits * LAGR;
     const double* y = reinterpret_cast<const double*>(zz + ((size_t)p * C + c) * N) + kind;
     double R[LAGR];
     for (int l = 0; l < LAGR; ++l) R[l] = 0.0;
     for (uint32_t u = 0; u < g.nunits; ++u)
-      for (int l = 0; l < LAGR; ++l) R[l] += pc[(size_t)u * LAGR + l];
+      for (int l = 0; l < LAGR; ++l) R[l] += __ldcg(&pc[(size_t)u * LAGR + l]);
     const double mf = st.cmean[(size_t)item * C + c], sum = st.csum[(size_t)item * C + c];
-    double hs = st.head[(size_t)item * C + c], ts = st.tail[(size_t)item * C + c];
+    double hs = __ldcg(&st.head[(size_t)item * C + c]), ts = __ldcg(&st.tail[(size_t)item * C + c]);
     for (int l = 0; l < LAGR; ++l) {
       const uint32_t t = t0 + l;
       if (t < N) {
@@ -699,10 +681,10 @@ __global__ void __launch_bounds__(DEC_NT) k_decide_r(const double2* __restrict__
     st.head[(size_t)item * C + c] = hs;
     st.tail[(size_t)item * C + c] = ts;
   }
-  dec_reduce(vals, LAGR, red, tot);
+  dec_reduce<NT>(vals, LAGR, red, tot);
   if (threadIdx.x == 0) {
     const size_t o = (size_t)kind * PB + p;
-    double rho_sum = st.rhosum[item];
+    double rho_sum = __ldcg(&st.rhosum[item]);
     long long lag = (long long)N;
     if (!st.geyer) {
       if (rho_walk(tot, LAGR, t0, N, C, st.varhat[item], rho_sum, lag)) {
@@ -713,7 +695,7 @@ __global__ void __launch_bounds__(DEC_NT) k_decide_r(const double2* __restrict__
         st.wl[cur ^ 1][atomicAdd(&st.nwl[cur ^ 1], 1)] = item;
       }
     } else {
-      double pend = st.gpend[item], prev = st.gprev[item];
+      double pend = __ldcg(&st.gpend[item]), prev = __ldcg(&st.gprev[item]);
       if (geyer_walk(tot, LAGR, t0, N, C, st.varhat[item], rho_sum, pend, prev, lag)) {
         st.ess[o] = geyer_ess((double)C * (double)N, rho_sum);
         st.lag[o] = lag;
@@ -724,6 +706,79 @@ __global__ void __launch_bounds__(DEC_NT) k_decide_r(const double2* __restrict__
         st.wl[cur ^ 1][atomicAdd(&st.nwl[cur ^ 1], 1)] = item;
       }
     }
+  }
+  __syncthreads();  // red / tot are free for the CTA's next item
+}
+
+// ---------------------------------------------------------------- all later rounds in ONE launch
+// Persistent cooperative grid (every CTA resident): per round of 32 lags, the CTAs stride over the work
+// units of the listed (parameter, kind) items, a grid-wide barrier, the CTAs stride over the items'
+// decisions (which build the next list), a grid-wide barrier.  The loop ends on the device when the list is
+// empty or no lag is left -- the host neither reads the list length nor synchronises between rounds
+// (round 1's driver copied `nwork` back and blocked before every round).
+struct RoundsSmem {
+  union {
+    MoR1Smem r1;
+    MoRSmem r;
+  } m;
+  double red[MO_CTA / 32][DEC_RED];
+  double tot[DEC_RED];
+  uint64_t bar;  // the one mbarrier both tile variants signal (its phase is carried across units and rounds)
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target) {
+  // all CTAs are co-resident (cooperative launch).  Monotone counter: barrier k completes at k * gridDim.x.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t_start = clock64();
+    while (*(volatile unsigned int*)bar < target) {
+      if (clock64() - t_start > 20000000000ll) {  // ~10 s: a protocol bug traps instead of hanging the GPU
+        printf("b200ref: grid barrier timed out (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MO_CTA, 2) k_ess_rounds(const double2* __restrict__ zz, ChainGeom g, int PB, ChainState st,
+                                                          unsigned int* gbar) {
+  extern __shared__ __align__(128) unsigned char mo_smem_raw[];
+  RoundsSmem& S = *reinterpret_cast<RoundsSmem*>(mo_smem_raw);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&S.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  unsigned int target = 0;
+  const uint32_t upi = g.C * g.nunits;  // work units per listed item
+  int cur = 0;
+  for (uint32_t t0 = 1 + LAGB; t0 < g.N; t0 += LAGR, cur ^= 1) {
+    const int nwork = __ldcg(&st.nwl[cur]);  // final since the barrier that ended the previous round
+    if (nwork == 0) break;                   // uniform over the grid
+    const uint64_t total = (uint64_t)nwork * upi;
+    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+      const int li = (int)(w / upi);
+      const uint32_t cu = (uint32_t)(w - (uint64_t)li * upi);
+      const uint32_t c = cu / g.nunits, u = cu - c * g.nunits;
+      const int item = __ldcg(&st.wl[cur][li]);
+      const int p = item >> 1, kind = item & 1;
+      const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
+      double* out = st.partr + (((size_t)li * g.C + c) * g.nunits + u) * LAGR;
+      if (t0 <= (uint32_t)MO_T0MAX) moments_r1_unit(S.m.r1, zc, g, t0, kind, u, out, &S.bar, phase);
+      else moments_r_unit(S.m.r, zc, g, t0, kind, u, out, &S.bar, phase);
+    }
+    if (blockIdx.x == 0 && tid == 0) st.nwl[cur ^ 1] = 0;  // the list the decisions are about to build
+    grid_barrier(gbar, target);
+    for (int li = blockIdx.x; li < nwork; li += gridDim.x)
+      decide_r_item<MO_CTA>(zz, g, PB, t0, cur, li, st, S.red, S.tot);
+    grid_barrier(gbar, target);
   }
 }
 

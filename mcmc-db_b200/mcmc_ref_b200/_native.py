@@ -14,6 +14,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libb200ref.so"
 
 ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_NONFINITE = -1, -2, -3, -4
 SUMMARY_K = 20
+S_FLAGS = 15  # B200REF_S_FLAGS: bit0 mean passed, bit1 std passed
 MAX_QUANTILES = 8
 ESS_MODES = {"first_negative": 0, "geyer": 1}
 GLM_FAMILIES = {"bernoulli_logit": 0, "binomial_logit": 1, "poisson_log": 2, "normal": 3}

@@ -41,6 +41,17 @@ def _stream_ptr() -> int:
     return int(torch.cuda.current_stream().cuda_stream)
 
 
+def _quantile_levels(quantiles) -> list[float]:
+    """numpy.quantile (backends_numpy.py:44) raises for levels outside [0, 1]; so does this backend."""
+    qs = [float(q) for q in quantiles]
+    if len(qs) > _native.MAX_QUANTILES:
+        raise ValueError(f"at most {_native.MAX_QUANTILES} quantile levels per call; got {len(qs)}")
+    for q in qs:
+        if not 0.0 <= q <= 1.0:  # NaN fails both comparisons
+            raise ValueError("Quantiles must be in the range [0, 1]")
+    return qs
+
+
 class Workspace:
     """Caller-owned scratch the library carves its buffers from (grows on demand)."""
 
@@ -121,7 +132,7 @@ def diagnostics_batch(x, quantiles=_DEFAULT_Q, workspace: Workspace | None = Non
     lib = _native.load()
     xt = to_device(x)
     p, c, n = xt.shape
-    qs = [float(q) for q in quantiles]
+    qs = _quantile_levels(quantiles)
     t, o = _alloc_outputs(p, len(qs), True, xt.device)
     if p == 0:
         return t
@@ -143,7 +154,7 @@ def stats_batch(x, quantiles=_DEFAULT_Q, workspace: Workspace | None = None) -> 
     if xt.dim() == 3:
         xt = xt.reshape(xt.shape[0], -1)
     p, m = xt.shape
-    qs = [float(q) for q in quantiles]
+    qs = _quantile_levels(quantiles)
     t, o = _alloc_outputs(p, len(qs), False, xt.device)
     if p == 0:
         return t

@@ -66,11 +66,24 @@ def compare_stats(
     return CompareResult(passed=len(failures) == 0, details=details, failures=failures)
 
 
+def _nonfinite_stats(row: np.ndarray) -> dict[str, float]:
+    """Candidate draws holding NaN / inf (a diverged sampler -- the case the tool exists to flag).  The reference's
+    pure-Python ``sum(values) / n`` gives nan or +-inf for the mean and ``(inf - inf)**2`` = nan for the spread
+    (compare.py:58-64); ``compare_stats`` then reports ``rel_error=nan > tol`` and the verdict is a FAILED compare,
+    not an exception.  No arithmetic on the draws is needed for that answer."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        mean = float(np.sum(row) / row.size)
+    return {"mean": mean, "std": float("nan")}
+
+
 def compute_basic_stats(values: Sequence[float]) -> dict[str, float]:
     n = len(values)
     if n == 0:
         return {"mean": float("nan"), "std": float("nan")}
-    out = batch.stats_batch(np.asarray(values, dtype=np.float64).reshape(1, n), quantiles=())
+    row = np.asarray(values, dtype=np.float64).reshape(n)
+    if not np.isfinite(row).all():
+        return _nonfinite_stats(row)
+    out = batch.stats_batch(row.reshape(1, n), quantiles=())
     return {"mean": float(out["mean"][0].item()), "std": float(out["std"][0].item())}
 
 
@@ -86,9 +99,14 @@ def compute_stats_from_draws(draws: Mapping[str, Sequence[float]]) -> dict[str, 
                 result[p] = {"mean": float("nan"), "std": float("nan")}
             continue
         x = np.stack([np.asarray(draws[p], dtype=np.float64) for p in params])
-        out = batch.stats_batch(x, quantiles=())
-        mean = out["mean"].cpu().numpy()
-        std = out["std"].cpu().numpy()
-        for i, p in enumerate(params):
-            result[p] = {"mean": float(mean[i]), "std": float(std[i])}
+        finite = np.isfinite(x).all(axis=1)
+        for i in np.flatnonzero(~finite):  # one bad parameter fails its own compare, not the whole batch
+            result[params[i]] = _nonfinite_stats(x[i])
+        good = np.flatnonzero(finite)
+        if good.size:
+            out = batch.stats_batch(x[good] if good.size < len(params) else x, quantiles=())
+            mean = out["mean"].cpu().numpy()
+            std = out["std"].cpu().numpy()
+            for j, i in enumerate(good):
+                result[params[i]] = {"mean": float(mean[j]), "std": float(std[j])}
     return {p: result[p] for p in draws}

@@ -38,6 +38,22 @@ def _host_tensor(arr: np.ndarray) -> torch.Tensor:
         return torch.from_numpy(arr)
 
 
+_PINNED: list[torch.Tensor] = []
+_PINNED_DONE: list = []
+
+
+def _pinned_slabs(m: int):
+    """Two pinned float64 staging slabs of at least m elements and the events of their last H2D copies (kept for
+    the life of the process, grown on demand)."""
+    if not _PINNED_DONE:
+        _PINNED_DONE[:] = [torch.cuda.Event(), torch.cuda.Event()]
+    if not _PINNED or _PINNED[0].numel() < m:
+        for ev in _PINNED_DONE:
+            ev.synchronize()
+        _PINNED[:] = [torch.empty(max(m, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
+    return _PINNED, _PINNED_DONE
+
+
 def chain_geometry(chain: np.ndarray) -> tuple[int, int]:
     """(n_chains, draws per chain); ragged chains are rejected (documented divergence)."""
     if chain.size == 0:
@@ -68,8 +84,15 @@ def table_to_device(table, params: Iterable[str]) -> tuple[torch.Tensor, int, in
     c, n = chain_geometry(chain)
     m = c * n
     x = torch.empty((len(params), m), dtype=torch.float64, device=dev)
-    for i, name in enumerate(params):  # one H2D copy per Arrow column, no host-side restacking
-        x[i].copy_(_host_tensor(_np_column(table, name, np.float64)), non_blocking=True)
+    # Arrow column buffers are pageable: each column is staged through one of two PINNED slabs so that the H2D
+    # copies run at PCIe speed and overlap the host-side copy of the next column
+    stage, done = _pinned_slabs(m)
+    for i, name in enumerate(params):
+        b = i & 1
+        done[b].synchronize()  # the slab's previous copy (this call's or an earlier one's) has left the host
+        stage[b][:m].copy_(_host_tensor(_np_column(table, name, np.float64)))
+        x[i].copy_(stage[b][:m], non_blocking=True)
+        done[b].record()
     if m > 1 and params:
         sorted_rows, _ = rows_in_order(_host_tensor(chain).to(dev), _host_tensor(draw).to(dev))
         if not sorted_rows:

@@ -68,3 +68,27 @@ def glm_lp(family: str, X, y, beta, trials=None, sigma=None, workspace: batch.Wo
                                          st.data_ptr() if st is not None else None, n, d, s, lp.data_ptr(),
                                          ws.data_ptr(), ws.numel(), batch._stream_ptr()))
     return lp
+
+
+def glm_lp_sharded(family: str, X, y, beta_local, n_draws: int | None = None, trials=None, sigma_local=None,
+                   group=None, workspace: batch.Workspace | None = None) -> torch.Tensor:
+    """Draw-block sharded ``glm_lp``: every rank holds the design ``X`` / ``y`` (replicated once,
+    see ``broadcast_design``) and ITS contiguous block of the draws (``sharding.shard_bounds(n_draws, world, rank)``;
+    ``sigma_local`` likewise for the normal family); each evaluates its block on its own GPU and one all_gather
+    of the S log-densities gives every rank ``lp[S]`` in draw order.  Single process: same as ``glm_lp``."""
+    from . import sharding
+
+    lp_local = glm_lp(family, X, y, beta_local, trials=trials, sigma=sigma_local, workspace=workspace)
+    return sharding.gather_draw_blocks(lp_local, n_draws, group)
+
+
+def broadcast_design(X, y, src: int = 0, group=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Replicate the design matrix and response from rank ``src`` to every rank (untimed setup; 205 MB for config 3).
+    Every rank passes tensors of the right shape; the contents of the non-source ranks are overwritten."""
+    import torch.distributed as dist
+
+    xt, yt = batch.to_device(X), batch.to_device(y).reshape(-1)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(xt, src=src, group=group)
+        dist.broadcast(yt, src=src, group=group)
+    return xt, yt

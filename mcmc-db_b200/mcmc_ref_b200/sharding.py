@@ -2,8 +2,10 @@
 
 One process per GPU (torch.distributed; NCCL on GPUs, gloo in the CPU tests).  There is no
 data-path collective: each rank runs the full pass on its contiguous block of parameters;
-the only communication is one all_gather of the [P_local, 20] summary rows and one
-all_reduce(MIN) of the compare verdict.
+the only communication is ONE all_gather of the [P_local, 20] summary rows into a pre-allocated
+buffer.  The global compare verdict is the AND of the gathered flags column, computed
+on the device and read only when somebody asks for it as a bool -- no second collective, no host
+synchronisation inside the step.
 """
 
 from __future__ import annotations
@@ -38,7 +40,7 @@ def gather_summaries(local: torch.Tensor, n_params: int | None = None, group=Non
     if local.shape[0] != sizes[rank]:
         raise ValueError(f"rank {rank} holds {local.shape[0]} parameters, expected {sizes[rank]}")
     if len(set(sizes)) == 1:
-        out = torch.empty((sum(sizes), k), dtype=local.dtype, device=local.device)
+        out = _gather_buffer(sum(sizes), k, local.dtype, local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
     pad = max(sizes)
@@ -47,6 +49,43 @@ def gather_summaries(local: torch.Tensor, n_params: int | None = None, group=Non
     parts = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(parts, buf, group=group)
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+_GATHER_BUFFERS: dict = {}
+
+
+def _gather_buffer(rows: int, k: int, dtype, device) -> torch.Tensor:
+    """The gathered summary of a step lives in one buffer per (shape, device), allocated once."""
+    key = (rows, k, dtype, str(device))
+    buf = _GATHER_BUFFERS.get(key)
+    if buf is None:
+        buf = _GATHER_BUFFERS[key] = torch.empty((rows, k), dtype=dtype, device=device)
+    return buf
+
+
+class DeviceVerdict:
+    """Overall compare verdict held on the device; ``bool(v)`` is the first (and only) host read."""
+
+    __slots__ = ("flag",)
+
+    def __init__(self, flag: torch.Tensor) -> None:
+        self.flag = flag
+
+    def __bool__(self) -> bool:
+        return bool(self.flag.item())
+
+    def __repr__(self) -> str:
+        return f"DeviceVerdict({bool(self)})"
+
+
+def verdict_from_summary(summary: torch.Tensor, flags_col: int | None = None) -> DeviceVerdict:
+    """AND over all parameters of (mean passed & std passed) -- compare.py:54 -- from the summary's flags
+    column (bit0 mean, bit1 std; include/b200ref.h B200REF_S_FLAGS).  Stays on the device."""
+    if flags_col is None:
+        from . import _native
+
+        flags_col = _native.S_FLAGS
+    return DeviceVerdict((summary[:, flags_col] == 3.0).all())
 
 
 def all_passed(local_ok: bool, device=None, group=None) -> bool:
@@ -58,10 +97,23 @@ def all_passed(local_ok: bool, device=None, group=None) -> bool:
     return bool(t.item())
 
 
+def gather_draw_blocks(local: torch.Tensor, n_draws: int | None = None, group=None) -> torch.Tensor:
+    """All ranks receive the per-draw values (log-densities) of all draws, in draw order: rank r holds the
+    contiguous block ``shard_bounds(n_draws, world, r)`` (draws are independent, the
+    only communication is this gather of S doubles)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    return gather_summaries(local.reshape(-1, 1), n_draws, group).reshape(-1)
+
+
 def full_pass_sharded(cand_local, ref_local, n_params: int | None = None, tolerance: float = 0.15, group=None,
                       **kw) -> tuple[torch.Tensor, bool]:
-    """Full diagnostics + compare pass on this rank's parameter block, then the small gather."""
+    """Full diagnostics + compare pass on this rank's parameter block, then the one small gather.  With more than
+    one rank the verdict is a ``DeviceVerdict`` (truth-testable; reading it is the only host synchronisation)."""
     from . import batch
 
     summary, ok = batch.full_pass(cand_local, ref_local, tolerance=tolerance, **kw)
-    return gather_summaries(summary, n_params, group), all_passed(ok, summary.device, group)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return summary, ok
+    gathered = gather_summaries(summary, n_params, group)
+    return gathered, verdict_from_summary(gathered)

@@ -44,6 +44,47 @@ def _worker(args):
         sr.close()
 
 
+def _ref_worker(args):
+    """One parameter block through the REFERENCE ITSELF (oracle/_ref/mcmc_ref, the unmodified package):
+    split_rhat + ess_bulk + ess_tail (diagnostics.py:13-73), NumpyBackend.stats of candidate and reference
+    draws (backends_numpy.py:17-49), compute_stats_from_draws + compare_stats (compare.py:24-68) --
+    BASELINE.md section 4, step 2."""
+    cand_name, cand_shape, ref_name, ref_shape, lo, hi, tol = args
+    import pyarrow as pa
+
+    from oracle.build_ref import import_reference
+
+    if import_reference() is None:
+        raise RuntimeError("oracle/_ref is not built (python oracle/build_ref.py)")
+    from mcmc_ref import compare as rc
+    from mcmc_ref import diagnostics as rd
+    from mcmc_ref.backends_numpy import NumpyBackend
+
+    sc = shared_memory.SharedMemory(name=cand_name)
+    sr = shared_memory.SharedMemory(name=ref_name)
+    try:
+        cand = np.ndarray(cand_shape, dtype=np.float64, buffer=sc.buf)
+        ref = np.ndarray(ref_shape, dtype=np.float64, buffer=sr.buf)
+        rows = np.empty((hi - lo, len(KEYS)))
+        ok = True
+        be = NumpyBackend()
+        for j, p in enumerate(range(lo, hi)):
+            chains = cand[p].tolist()
+            flat = [v for ch in chains for v in ch]
+            rh, eb, et = rd.split_rhat(chains), rd.ess_bulk(chains), rd.ess_tail(chains)
+            cs = be.stats(pa.table({"x": cand[p].reshape(-1)}), ["x"])["x"]
+            rs = be.stats(pa.table({"x": ref[p]}), ["x"])
+            act = rc.compute_stats_from_draws({"x": flat})
+            res = rc.compare_stats(rs, act, tol, ("mean", "std"))
+            ok = ok and res.passed
+            rows[j] = (rh, eb, et, act["x"]["mean"], act["x"]["std"], cs["q5"], cs["q50"], cs["q95"],
+                       rs["x"]["mean"], rs["x"]["std"], rs["x"]["q5"], rs["x"]["q50"], rs["x"]["q95"])
+        return lo, rows, ok
+    finally:
+        sc.close()
+        sr.close()
+
+
 class OraclePool:
     """Spawned worker pool + shared-memory staging of one sample."""
 
@@ -66,18 +107,23 @@ class OraclePool:
         self._staged = out
         return out
 
-    def run(self, tolerance: float = 0.15, chunk: int = 1):
-        """One oracle pass over the staged sample.  Returns (seconds, dict of [P] arrays)."""
+    def run(self, tolerance: float = 0.15, chunk: int = 1, impl: str = "port"):
+        """One pass over the staged sample: impl "port" = oracle/mcmc_oracle.py (vectorised numpy restatement),
+        "reference" = the unmodified reference package in oracle/_ref.  Returns (seconds, dict of [P] arrays)."""
         from oracle import mcmc_oracle as O
 
         (cn, cs), (rn, rs) = self._staged
         p = cs[0]
-        tasks = [(cn, cs, rn, rs, lo, min(lo + chunk, p)) for lo in range(0, p, chunk)]
         t0 = time.perf_counter()
-        parts = self.pool.map(_worker, tasks, chunksize=1)
         rows = np.empty((p, len(KEYS)))
-        for lo, r in parts:
-            rows[lo:lo + len(r)] = r
+        if impl == "reference":
+            tasks = [(cn, cs, rn, rs, lo, min(lo + chunk, p), tolerance) for lo in range(0, p, chunk)]
+            for lo, r, _ in self.pool.map(_ref_worker, tasks, chunksize=1):
+                rows[lo:lo + len(r)] = r
+        else:
+            tasks = [(cn, cs, rn, rs, lo, min(lo + chunk, p)) for lo in range(0, p, chunk)]
+            for lo, r in self.pool.map(_worker, tasks, chunksize=1):
+                rows[lo:lo + len(r)] = r
         out = {k: rows[:, i] for i, k in enumerate(KEYS)}
         out["rel_mean"], out["pass_mean"] = O.compare_arrays(out["ref_mean"], out["mean"], tolerance)
         out["rel_std"], out["pass_std"] = O.compare_arrays(out["ref_std"], out["std"], tolerance)

@@ -1,0 +1,218 @@
+"""GPU parity tests added in round 2 (all through the Python mirror -> ctypes -> C-ABI):
+
+* BASELINE config 1 as a compare SCENARIO: chains 0-3 of the packaged eight_schools model against all ten packaged
+  chains through `reference.compare` (fixture `c1_compare.json`, produced by the unmodified reference).
+* the reference's arrow backend as a cross-check of `B200Backend.stats` (tests/unit/test_backends_consistency.py:17-28).
+* value parity of the long-chain paths (wide partition, binned score scatter, oversize-bucket list overflow).
+* error behaviour: quantile levels outside [0, 1], non-finite candidate draws in a compare, 4096 chains.
+"""
+
+from __future__ import annotations
+
+import json
+import math
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, close
+from oracle import mcmc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def B():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as g
+
+    g.build()
+    from mcmc_ref_b200 import batch
+
+    return batch
+
+
+def _write_packaged(root, model, draws, params):
+    """The reference's packaged layout (draws/<model>.draws.parquet: chain, draw int64 + one double column per param)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    p, c, n = draws.shape
+    cols = {"chain": pa.array(np.repeat(np.arange(c), n), type=pa.int64()),
+            "draw": pa.array(np.tile(np.arange(n), c), type=pa.int64())}
+    for i, name in enumerate(params):
+        cols[name] = pa.array(draws[i].reshape(-1), type=pa.float64())
+    (root / "draws").mkdir(parents=True, exist_ok=True)
+    pq.write_table(pa.table(cols), root / "draws" / f"{model}.draws.parquet")
+
+
+def test_c1_compare_scenario(B, packaged_subset, tmp_path):
+    """BASELINE configs[0]: 10 params x 4 chains x 1000 candidate draws vs the packaged reference posterior."""
+    from mcmc_ref_b200 import reference
+    from mcmc_ref_b200.store import PackagedStore
+
+    gold = json.loads((GOLDEN / "c1_compare.json").read_text())
+    arrays, meta = packaged_subset
+    model = gold["model"]
+    params = meta[model]["params"]
+    assert params == gold["params"]
+    draws = arrays[model]  # [10 params, 10 chains, 1000 draws]
+    _write_packaged(tmp_path, model, draws, params)
+    store = PackagedStore(local_root=tmp_path / "none", packaged_root=tmp_path)
+    actual = {p: draws[i, :4].reshape(-1).tolist() for i, p in enumerate(params)}
+    res = reference.compare(model, actual, tolerance=gold["tolerance"], store=store)
+    want = gold["compare"]["numpy"]
+    assert res.passed is want["passed"] is True and res.failures == want["failures"]
+    for p in params:
+        for m in ("mean", "std"):
+            g, w = res.details[p][m], want["details"][p][m]
+            assert g.passed is w["passed"]
+            for k in ("ref", "actual", "rel_error"):
+                assert close(getattr(g, k), w[k], 1e-12), (p, m, k, getattr(g, k), w[k])
+    # the arrow backend of the reference gives the same verdicts (its quantiles differ by an ulp, mean / std do not)
+    assert gold["compare"]["arrow"]["passed"] is True
+    # same inputs at a tolerance they cannot meet: the reference's failure strings, in its order
+    tight = reference.compare(model, actual, tolerance=gold["compare_tight"]["tolerance"], store=store)
+    assert tight.passed is False and tight.failures == gold["compare_tight"]["failures"]
+    # the candidate's own diagnostics and numpy statistics
+    d = B.diagnostics_batch(draws[:, :4])
+    for i, p in enumerate(params):
+        for k in ("rhat", "ess_bulk", "ess_tail"):
+            assert close(float(d[k][i].item()), gold["candidate_diagnostics"][p][k], TOL), (p, k)
+        ns = gold["candidate_numpy_stats"][p]
+        assert close(float(d["mean"][i].item()), ns["mean"], 1e-12) and close(float(d["std"][i].item()), ns["std"], 1e-12)
+        for j, q in enumerate(("q5", "q50", "q95")):
+            assert float(d["quantiles"][i, j].item()) == ns[q], (p, q)
+
+
+def test_arrow_backend_cross_check(B, packaged_subset):
+    """`ArrowBackend.stats` (backends_arrow.py:36-51) vs the b200 backend on the same table: mean / std to 1e-10
+    relative as the reference's own consistency test asks (test_backends_consistency.py:17-28); the linear quantiles
+    of pyarrow differ from numpy's `_lerp` by at most one ulp."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    from mcmc_ref_b200.backends import get_backend
+
+    arrays, meta = packaged_subset
+    rng = np.random.default_rng(17)
+    tables = {m: (arrays[m].reshape(arrays[m].shape[0], -1), meta[m]["params"]) for m in arrays.files}
+    tables["synthetic_100"] = (rng.standard_normal((1, 100)), ["x"])  # the reference test's own size
+    be = get_backend("b200")
+    for name, (x, params) in tables.items():
+        table = pa.table({p: x[i] for i, p in enumerate(params)})
+        got = be.stats(table, params)
+        for i, p in enumerate(params):
+            col = table.column(p)
+            a_mean = pc.mean(col).as_py()
+            a_std = pc.stddev(col, ddof=0).as_py()
+            a_q = pc.quantile(col, q=[0.05, 0.5, 0.95], interpolation="linear", skip_nulls=True).to_pylist()
+            assert abs(got[p]["mean"] - a_mean) <= 1e-10 * max(abs(a_mean), 1e-300), (name, p)
+            assert abs(got[p]["std"] - a_std) <= 1e-10 * max(abs(a_std), 1e-300), (name, p)
+            for key, aq in zip(("q5", "q50", "q95"), a_q):
+                ulp = math.ulp(max(abs(aq), abs(got[p][key])))
+                assert abs(got[p][key] - aq) <= ulp, (name, p, key, got[p][key], aq)
+
+
+def _check_vs_oracle(B, x, label, lags=True):
+    d = B.diagnostics_batch(x[None])
+    want = O.diagnostics_param(x)
+    for k in ("rhat", "ess_bulk", "ess_tail"):
+        assert close(float(d[k][0].item()), want[k], TOL), (label, k, float(d[k][0].item()), want[k])
+    if lags:
+        assert int(d["lag_bulk"][0].item()) == want["lag_bulk"] and int(d["lag_tail"][0].item()) == want["lag_tail"], label
+    ns = O.numpy_stats(x.reshape(-1))
+    for j, q in enumerate(("q5", "q50", "q95")):
+        assert float(d["quantiles"][0, j].item()) == ns[q], (label, q)
+    assert close(float(d["mean"][0].item()), ns["mean"], 1e-12), label
+
+
+def test_long_chain_binned_scatter_vs_oracle(B):
+    """M > 3M pooled draws in diagnostics mode: wide partition + two-step (binned) score scatter.  Folded scores,
+    tail R-hat and tail ESS of that path against the oracle -- continuous, and with ties (values rounded)."""
+    rng = np.random.default_rng(2024)
+    c, n = 4, 1_000_000
+    from scipy.signal import lfilter
+
+    phi = 0.5
+    x = lfilter([math.sqrt(1 - phi * phi)], [1.0, -phi], rng.standard_normal((c, n)), axis=1)  # AR(1) chains
+    _check_vs_oracle(B, x, "binned_continuous")
+    _check_vs_oracle(B, np.round(x, 3), "binned_tied")
+
+
+def test_oversize_list_overflow_falls_back_cleanly(B):
+    """More oversize sub-buckets than the list holds (600 values repeated ~5000 times on the wide path): k_finish_big
+    must read only the stored entries and the parameter must come out of the LSD fallback with exact results."""
+    rng = np.random.default_rng(7)
+    x = rng.integers(0, 600, (4, 750_000)).astype(np.float64)
+    _check_vs_oracle(B, x, "600_values_x_5000")
+
+
+def test_average_bucket_over_capacity(B):
+    """~17M pooled draws in one parameter: the average sub-bucket exceeds the on-chip capacity."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((4, 4_300_000))
+    d = B.diagnostics_batch(x[None])
+    flat = np.sort(x.reshape(-1))
+    ns = O.numpy_stats(x.reshape(-1))
+    for j, q in enumerate(("q5", "q50", "q95")):
+        assert float(d["quantiles"][0, j].item()) == ns[q], q
+    m = flat.size
+    assert 0.999 < float(d["rhat"][0].item()) < 1.001
+    assert 0.5 * m < float(d["ess_bulk"][0].item()) <= m and 0.5 * m < float(d["ess_tail"][0].item()) <= m
+    # rank-normalised R-hat of the bulk against the oracle on the same data (one pooled sort on the host)
+    want = O.diagnostics_param(x)
+    for k in ("rhat", "ess_bulk", "ess_tail"):
+        assert close(float(d[k][0].item()), want[k], TOL), (k, float(d[k][0].item()), want[k])
+
+
+def test_4096_chains(B):
+    """The advertised chain limit: k_decide0 keeps 3 doubles per chain in (opted-in) dynamic shared memory."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((4096, 8))
+    d = B.diagnostics_batch(x[None])
+    want = O.diagnostics_param(x)
+    for k in ("rhat", "ess_bulk", "ess_tail"):
+        assert close(float(d[k][0].item()), want[k], TOL), (k, float(d[k][0].item()), want[k])
+    with pytest.raises(ValueError, match="chains"):
+        B.diagnostics_batch(rng.standard_normal((1, 4097, 2)))
+
+
+def test_quantile_levels_validated(B):
+    x = np.random.default_rng(1).standard_normal((2, 500))
+    for bad in (-0.1, 1.5, float("nan")):
+        with pytest.raises(ValueError, match=r"range \[0, 1\]"):
+            B.stats_batch(x, quantiles=(0.5, bad))
+        with pytest.raises(ValueError, match=r"range \[0, 1\]"):
+            B.diagnostics_batch(x.reshape(2, 4, 125), quantiles=(bad,))
+    out = B.stats_batch(x, quantiles=(0.0, 1.0))
+    assert np.array_equal(out["quantiles"].cpu().numpy(), np.stack([x.min(axis=1), x.max(axis=1)], axis=1))
+
+
+def test_compare_with_nonfinite_candidate_is_a_failed_verdict(B):
+    """A diverged sampler (NaN / inf draws) must FAIL the compare with the reference's failure strings
+    (compare.py:38-51, :58-64: mean nan or +-inf, std nan, `rel_error=nan > tol`), not raise -- and one bad parameter
+    must not take the others with it."""
+    from mcmc_ref_b200.compare import compare_stats, compute_basic_stats, compute_stats_from_draws
+
+    rng = np.random.default_rng(3)
+    good = rng.standard_normal(400).tolist()
+    bad_nan = list(good)
+    bad_nan[7] = float("nan")
+    bad_inf = list(good)
+    bad_inf[9] = float("inf")
+    act = compute_stats_from_draws({"a": good, "b": bad_nan, "c": bad_inf})
+    assert math.isfinite(act["a"]["mean"]) and math.isnan(act["b"]["mean"]) and math.isnan(act["b"]["std"])
+    assert act["c"]["mean"] == math.inf and math.isnan(act["c"]["std"])
+    ref = {k: {"mean": float(np.mean(good)), "std": float(np.std(good))} for k in "abc"}
+    res = compare_stats(ref, act, 0.15, ("mean", "std"))
+    assert res.passed is False
+    assert res.failures == ["b.mean rel_error=nan > 0.15", "b.std rel_error=nan > 0.15",
+                            "c.mean rel_error=inf > 0.15", "c.std rel_error=nan > 0.15"]
+    assert res.details["a"]["mean"].passed and res.details["a"]["std"].passed
+    s = compute_basic_stats(bad_nan)
+    assert math.isnan(s["mean"]) and math.isnan(s["std"])

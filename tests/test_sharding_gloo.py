@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mcmc_ref_b200.sharding import all_passed, gather_summaries, shard_bounds
+from mcmc_ref_b200.sharding import all_passed, gather_draw_blocks, gather_summaries, shard_bounds, verdict_from_summary
 
 
 def test_shard_bounds_cover_everything():
@@ -46,7 +46,18 @@ def _worker(rank: int, world: int, port: int, n_params: int, q):
         ok_auto = bool(torch.equal(full2, want))
         v_all = all_passed(True)
         v_one = all_passed(rank != 1)
-        q.put((rank, ok_order, ok_auto, v_all, v_one))
+        # ONE collective per step: the verdict is the AND of the gathered flags column (column 15, value 3 =
+        # mean and std passed); rank 1's last parameter fails in the second variant
+        flags = torch.full((hi - lo, 20), 3.0, dtype=torch.float64)
+        v_col_all = bool(verdict_from_summary(gather_summaries(flags, n_params).clone()))
+        if rank == 1:
+            flags[-1, 15] = 1.0
+        v_col_one = bool(verdict_from_summary(gather_summaries(flags, n_params)))
+        # draw-block gather of the sharded log-density (value = draw index)
+        dlo, dhi = shard_bounds(2 * n_params + 1, world, rank)
+        lp = gather_draw_blocks(torch.arange(dlo, dhi, dtype=torch.float64), 2 * n_params + 1)
+        ok_lp = bool(torch.equal(lp, torch.arange(2 * n_params + 1, dtype=torch.float64)))
+        q.put((rank, ok_order, ok_auto, v_all, v_one, v_col_all, v_col_one, ok_lp))
     finally:
         dist.destroy_process_group()
 
@@ -64,6 +75,7 @@ def test_gather_and_verdict_world2(n_params):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok_order, ok_auto, v_all, v_one in results:
-        assert ok_order and ok_auto, rank
+    for rank, ok_order, ok_auto, v_all, v_one, v_col_all, v_col_one, ok_lp in results:
+        assert ok_order and ok_auto and ok_lp, rank
         assert v_all is True and v_one is False
+        assert v_col_all is True and v_col_one is False

@@ -116,6 +116,22 @@ int b200ref_diagnostics_ex_f64(const double* x_dev, int64_t P, int64_t C, int64_
                                const double* q_host, int nq, int ess_mode, const b200ref_outputs* out,
                                void* ws_dev, size_t ws_bytes, void* stream);
 
+/* The same diagnostics for draws in the reference's NUMPY layout: `Draws.to_numpy()` (draws.py:20-29) returns
+ * [rows][P] with rows ordered (chain, draw) and the PARAMETER index fastest.  x_rows_dev is that matrix
+ * ([C*N][P] fp64, device); the library transposes parameter blocks into its workspace (tiled transposing load)
+ * and runs the canonical path on them, so results are bit-identical to b200ref_diagnostics_ex_f64 on the
+ * transposed tensor.  Workspace: b200ref_rows_workspace_bytes (the canonical workspace of a parameter block
+ * plus the block's transposed draws; the library sizes the block to what it is given). */
+#define B200REF_LAYOUT_PCN 0  /* x[P][C][N], draw fastest (canonical: one Arrow / Parquet column per parameter) */
+#define B200REF_LAYOUT_ROWS 1 /* x[C*N][P], parameter fastest (Draws.to_numpy)                                 */
+size_t b200ref_rows_workspace_bytes(int64_t P, int64_t C, int64_t N);
+int b200ref_diagnostics_layout_f64(const double* x_dev, int layout, int64_t P, int64_t C, int64_t N,
+                                   const double* q_host, int nq, int ess_mode, const b200ref_outputs* out,
+                                   void* ws_dev, size_t ws_bytes, void* stream);
+/* out[p][r] = in[r][p0 + p] for PB parameter columns of an [M][P] row-major matrix (the transposing load itself). */
+int b200ref_transpose_rows_f64(const double* in_dev, int64_t M, int64_t P, int64_t p0, int64_t PB, double* out_dev,
+                               void* stream);
+
 /* mean / std(ddof=0) / numpy-linear quantiles over the pooled M draws of each of
  * P parameters; no diagnostics.  Replaces NumpyBackend.stats (backends_numpy.py:17-49).
  * Only out->mean, std, quantiles, order_stats, median are written. */

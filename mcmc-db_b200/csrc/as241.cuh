@@ -3,11 +3,13 @@
 // reference calls (diagnostics.py:124,131).  Every multiply and add is an explicit
 // round-to-nearest intrinsic so nvcc cannot contract a*b+c into an FMA: the
 // central branch (|p - 0.5| <= 0.425, 85 % of draws) is pure + * / and therefore
-// bit-identical to the CPU.  The tail branches go through log(); CUDA's log is
-// <= 1 ulp but not the host libm, so tail entries can differ from the stdlib in
-// the last place (measured and bounded in tests/test_gpu_parity.py).
+// bit-identical to the CPU.  The tail branches go through log(): the stdlib takes it from the C
+// library, and glibc's log (ARM Optimized Routines' table-driven algorithm, fused multiply-adds in the
+// build x86-64 CPUs with FMA run) is restated here operation by operation (`glibc_log`, constants in
+// log_table.cuh), so the tails are bit-identical to the stdlib too (tests: 0 ulp over the whole table).
 #pragma once
 #include "common.cuh"
+#include "log_table.cuh"
 
 namespace b200ref {
 
@@ -17,6 +19,35 @@ __device__ __forceinline__ double radd(double a, double b) { return __dadd_rn(a,
 #define B200REF_HORNER8(c0, c1, c2, c3, c4, c5, c6, c7, r)                                      \
   radd(rmul(radd(rmul(radd(rmul(radd(rmul(radd(rmul(radd(rmul(radd(rmul((c0), (r)), (c1)), (r)), \
        (c2)), (r)), (c3)), (r)), (c4)), (r)), (c5)), (r)), (c6)), (r)), (c7))
+
+__device__ const double kLogTab[256] = {B200REF_LOG_TABLE};
+
+// log(x) for normal x outside [1 - 2^-4, 1 + 0x1.09p-4): all the AS241 tails need (x <= 0.075).
+// x = 2^k z with z in [0x1.6p-1, 0x1.6p0); c_i = centre of z's subinterval; r = z / c_i - 1 (one fma on the
+// tabulated 1 / c_i); log x = k ln2 + log c_i + log1p(r), log1p by a degree-5 polynomial.  The fused and the
+// separately rounded operations are exactly those of glibc's FMA build (checked against its machine code and,
+// through the C restatement the tests load, against math.log on millions of points).
+__device__ __forceinline__ double glibc_log(double x) {
+  const uint64_t ix = (uint64_t)__double_as_longlong(x);
+  const uint64_t tmp = ix - 0x3fe6000000000000ull;
+  const int i = (int)((tmp >> 45) & 127u);
+  const long long k = (long long)tmp >> 52;
+  const double z = __longlong_as_double((long long)(ix - (tmp & (0xfffull << 52))));
+  const double invc = kLogTab[2 * i], logc = kLogTab[2 * i + 1];
+  const double r = __fma_rn(z, invc, -1.0);
+  const double kd = (double)k;
+  const double w = __fma_rn(kd, B200REF_LOG_LN2HI, logc);
+  const double hi = __dadd_rn(w, r);
+  const double lo = __fma_rn(kd, B200REF_LOG_LN2LO, __dadd_rn(__dsub_rn(w, hi), r));
+  const double r2 = __dmul_rn(r, r);
+  const double r3 = __dmul_rn(r, r2);
+  const double t1 = __fma_rn(r, B200REF_LOG_A2, B200REF_LOG_A1);
+  const double t2 = __fma_rn(r, B200REF_LOG_A4, B200REF_LOG_A3);
+  const double t3 = __fma_rn(r2, B200REF_LOG_A0, lo);
+  const double t4 = __fma_rn(t2, r2, t1);
+  const double t5 = __fma_rn(r3, t4, t3);
+  return __dadd_rn(t5, hi);
+}
 
 __device__ __forceinline__ double as241_inv_cdf(double p) {
   const double q = __dsub_rn(p, 0.5);
@@ -35,7 +66,7 @@ __device__ __forceinline__ double as241_inv_cdf(double p) {
     return radd(0.0, __ddiv_rn(num, den));
   }
   double r = (q <= 0.0) ? p : __dsub_rn(1.0, p);
-  r = __dsqrt_rn(-log(r));
+  r = __dsqrt_rn(-glibc_log(r));  // r <= 0.075: inside glibc_log's domain
   double num, den;
   if (r <= 5.0) {
     r = __dsub_rn(r, 1.6);

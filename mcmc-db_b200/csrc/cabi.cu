@@ -696,6 +696,67 @@ int b200ref_diagnostics_ex_f64(const double* x, int64_t P, int64_t C, int64_t N,
              (cudaStream_t)stream);
 }
 
+int b200ref_transpose_rows_f64(const double* in, int64_t M, int64_t P, int64_t p0, int64_t PB, double* out, void* stream) {
+  g_err[0] = 0;
+  if (M < 0 || P < 0 || PB < 0 || p0 < 0 || p0 + PB > P || ((M > 0 && PB > 0) && (!in || !out)))
+    return fail(B200REF_ERR_ARG, "bad transpose arguments");
+  if (M == 0 || PB == 0) return B200REF_OK;
+  if ((PB + TR_TILE - 1) / TR_TILE > 65535) return fail(B200REF_ERR_ARG, "transpose: at most %d parameters per call", 65535 * TR_TILE);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)((M + TR_TILE - 1) / TR_TILE), (unsigned)((PB + TR_TILE - 1) / TR_TILE));
+  LAUNCH(K_INGEST, st, k_transpose_rows<<<grid, TR_TILE * TR_ROWS, 0, st>>>(in, M, P, p0, PB, out));
+  CUDA_TRY(cudaGetLastError());
+  return B200REF_OK;
+}
+
+size_t b200ref_rows_workspace_bytes(int64_t P, int64_t C, int64_t N) {
+  if (P < 1) P = 1;
+  const int64_t pb = std::min<int64_t>(P, BATCH_CAP);
+  return b200ref_workspace_bytes(pb, C, N) + up((size_t)pb * (size_t)(C * N) * 8) + ALIGN;
+}
+
+int b200ref_diagnostics_layout_f64(const double* x, int layout, int64_t P, int64_t C, int64_t N, const double* q_host,
+                                   int nq, int ess_mode, const b200ref_outputs* out, void* ws, size_t ws_bytes,
+                                   void* stream) {
+  if (layout == B200REF_LAYOUT_PCN)
+    return b200ref_diagnostics_ex_f64(x, P, C, N, q_host, nq, ess_mode, out, ws, ws_bytes, stream);
+  g_err[0] = 0;
+  if (layout != B200REF_LAYOUT_ROWS) return fail(B200REF_ERR_ARG, "unknown layout %d", layout);
+  if (!out) return fail(B200REF_ERR_ARG, "null outputs");
+  if (nq > 0 && !q_host) return fail(B200REF_ERR_ARG, "null quantile levels");
+  if (ess_mode != B200REF_ESS_FIRST_NEGATIVE && ess_mode != B200REF_ESS_GEYER)
+    return fail(B200REF_ERR_ARG, "unknown ess_mode %d", ess_mode);
+  if (!x || P < 0 || C < 1 || N < 1) return fail(B200REF_ERR_ARG, "bad shape P=%lld C=%lld N=%lld", (long long)P, (long long)C, (long long)N);
+  if (P == 0) return B200REF_OK;
+  if (!ws) return fail(B200REF_ERR_WORKSPACE, "null workspace");
+  const int64_t M = C * N;
+  // parameter block: its transposed draws [pb][M] at the head of the workspace, the canonical workspace behind them
+  int64_t pb = std::min<int64_t>(P, BATCH_CAP);
+  const size_t min_ws = b200ref_workspace_min_bytes(C, N);
+  while (pb > 1 && up((size_t)pb * M * 8) + ALIGN + std::min(b200ref_workspace_bytes(pb, C, N), std::max(min_ws, ws_bytes / 2)) > ws_bytes) pb = (pb + 1) / 2;
+  const size_t head = up((size_t)pb * M * 8);
+  if (head + ALIGN + min_ws > ws_bytes) return fail(B200REF_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one transposed parameter block", ws_bytes);
+  char* base = (char*)(((uintptr_t)ws + ALIGN - 1) / ALIGN * ALIGN);
+  const size_t avail = ws_bytes - (size_t)(base - (char*)ws);
+  double* xt = (double*)base;
+  char* cws = base + head;
+  const size_t cws_bytes = avail - head;
+  Mode m{true, false, ess_mode == B200REF_ESS_GEYER};
+  for (int64_t p0 = 0; p0 < P; p0 += pb) {
+    const int64_t n = std::min<int64_t>(pb, P - p0);
+    int rc = b200ref_transpose_rows_f64(x, M, P, p0, n, xt, stream);
+    if (rc) return rc;
+    b200ref_outputs o = *out;  // this block's slices of the caller's outputs
+    auto adv = [&](auto*& ptr, int64_t stride) { if (ptr) ptr += p0 * stride; };
+    adv(o.rhat, 1); adv(o.rhat_bulk, 1); adv(o.rhat_tail, 1); adv(o.ess_bulk, 1); adv(o.ess_tail, 1);
+    adv(o.lag_bulk, 1); adv(o.lag_tail, 1); adv(o.mean, 1); adv(o.std, 1); adv(o.median, 1);
+    adv(o.quantiles, nq); adv(o.order_stats, 2 * (int64_t)nq);
+    rc = run(xt, n, C, N, q_host, nq, &o, nullptr, nullptr, nullptr, nullptr, m, cws, cws_bytes, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return B200REF_OK;
+}
+
 int b200ref_stats_f64(const double* x, int64_t P, int64_t M, const double* q_host, int nq,
                       const b200ref_outputs* out, void* ws, size_t ws_bytes, void* stream) {
   g_err[0] = 0;

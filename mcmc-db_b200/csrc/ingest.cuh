@@ -32,4 +32,28 @@ __global__ void k_gather_rows(const double* __restrict__ in, const int64_t* __re
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += stride) op[r] = ip[perm[r]];
 }
 
+// Transposing load of the reference's numpy layout: `Draws.to_numpy()` gives rows = (chain, draw), columns =
+// parameters, PARAMETER FASTEST (draws.py:20-29).  out[pb][r] = in[r][p0 + pb] for a block of PB parameter
+// columns: 32 x 32 tiles through padded shared memory, both the global reads (32 consecutive parameters of
+// a row = 256 B) and the global writes (32 consecutive rows of a parameter) are full sectors.  A TMA tensor
+// map is not used here: its global stride (8 P bytes) must be a multiple of 16 B, i.e. an even P.
+constexpr int TR_TILE = 32, TR_ROWS = 8;
+__global__ void __launch_bounds__(TR_TILE * TR_ROWS) k_transpose_rows(const double* __restrict__ in, int64_t M, int64_t P,
+                                                                      int64_t p0, int64_t PB, double* __restrict__ out) {
+  __shared__ double tile[TR_TILE][TR_TILE + 1];
+  const int64_t r0 = (int64_t)blockIdx.x * TR_TILE, c0 = (int64_t)blockIdx.y * TR_TILE;
+  const int tx = threadIdx.x & (TR_TILE - 1), ty = threadIdx.x / TR_TILE;
+#pragma unroll
+  for (int j = ty; j < TR_TILE; j += TR_ROWS) {
+    const int64_t r = r0 + j, c = c0 + tx;
+    if (r < M && c < PB) tile[j][tx] = in[r * P + p0 + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < TR_TILE; j += TR_ROWS) {
+    const int64_t c = c0 + j, r = r0 + tx;
+    if (c < PB && r < M) out[c * M + r] = tile[tx][j];
+  }
+}
+
 }  // namespace b200ref

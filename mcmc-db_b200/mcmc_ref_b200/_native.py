@@ -28,7 +28,9 @@ EXPORTS = (
     "b200ref_full_pass_workspace_bytes", "b200ref_full_pass_f64", "b200ref_full_pass_host_f64", "b200ref_synth_fill_f64",
     "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64", "b200ref_glm_lp_f64",
     "b200ref_row_order_i64", "b200ref_gather_rows_f64",
+    "b200ref_rows_workspace_bytes", "b200ref_diagnostics_layout_f64", "b200ref_transpose_rows_f64",
 )
+LAYOUTS = {"pcn": 0, "rows": 1}
 
 
 class Outputs(C.Structure):
@@ -91,6 +93,11 @@ def load() -> C.CDLL:
     lib.b200ref_glm_lp_f64.argtypes = [C.c_int, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, sz, vp]
     lib.b200ref_row_order_i64.argtypes = [vp, vp, i64, C.POINTER(C.c_int), vp]
     lib.b200ref_gather_rows_f64.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.b200ref_rows_workspace_bytes.restype = sz
+    lib.b200ref_rows_workspace_bytes.argtypes = [i64, i64, i64]
+    lib.b200ref_diagnostics_layout_f64.argtypes = [vp, C.c_int, i64, i64, i64, C.POINTER(dbl), C.c_int, C.c_int,
+                                                   C.POINTER(Outputs), vp, sz, vp]
+    lib.b200ref_transpose_rows_f64.argtypes = [vp, i64, i64, i64, i64, vp, vp]
     for name in EXPORTS:  # every symbol include/b200ref.h declares must be exported
         getattr(lib, name)
     _lib = lib

@@ -118,6 +118,35 @@ def _alloc_outputs(p: int, nq: int, diag: bool, dev) -> tuple[dict[str, torch.Te
     return t, o
 
 
+def diagnostics_rows(x_rows, n_chains: int, quantiles=_DEFAULT_Q, workspace: Workspace | None = None,
+                     ess_truncation: str = "first_negative") -> dict[str, torch.Tensor]:
+    """The same diagnostics for draws in the reference's numpy layout: ``x_rows[C * N, P]``, rows ordered
+    (chain, draw), PARAMETER fastest -- what ``Draws.to_numpy()`` / ``reference.draws(return_="numpy")`` return
+    (draws.py:20-29).  The library transposes parameter blocks on the device (tiled transposing load) and runs
+    the canonical path: bit-identical to ``diagnostics_batch`` of the transposed tensor."""
+    if ess_truncation not in _native.ESS_MODES:
+        raise ValueError(f"ess_truncation must be one of {sorted(_native.ESS_MODES)}; got {ess_truncation!r}")
+    lib = _native.load()
+    xt = to_device(x_rows)
+    if xt.dim() != 2:
+        raise ValueError(f"x_rows must be [C * N, P]; got shape {tuple(xt.shape)}")
+    rows, p = xt.shape
+    c = int(n_chains)
+    if c < 1 or rows % c:
+        raise ValueError(f"{rows} rows do not split into {n_chains} equal chains")
+    n = rows // c
+    qs = _quantile_levels(quantiles)
+    t, o = _alloc_outputs(p, len(qs), True, xt.device)
+    if p == 0:
+        return t
+    ws = (workspace or _WS).ensure(int(lib.b200ref_rows_workspace_bytes(p, c, n)))
+    qarr = (C.c_double * max(len(qs), 1))(*qs)
+    _native.check(lib.b200ref_diagnostics_layout_f64(xt.data_ptr(), _native.LAYOUTS["rows"], p, c, n, qarr, len(qs),
+                                                     _native.ESS_MODES[ess_truncation], C.byref(o),
+                                                     ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return t
+
+
 def diagnostics_batch(x, quantiles=_DEFAULT_Q, workspace: Workspace | None = None,
                       ws_cap_bytes: int | None = None, ess_truncation: str = "first_negative") -> dict[str, torch.Tensor]:
     """rhat / ess_bulk / ess_tail (+ mean, std, quantiles, median) for x[P, C, N].

@@ -216,3 +216,40 @@ def test_compare_with_nonfinite_candidate_is_a_failed_verdict(B):
     assert res.details["a"]["mean"].passed and res.details["a"]["std"].passed
     s = compute_basic_stats(bad_nan)
     assert math.isnan(s["mean"]) and math.isnan(s["std"])
+
+
+@pytest.mark.parametrize("m", [160_000, 262_144])
+def test_z_table_bit_exact_everywhere(B, m):
+    """All 2M - 1 entries of the device score table against `statistics.NormalDist().inv_cdf` (diagnostics.py:124-131),
+    tails included (0 ulp): a permutation visits every odd code k = 2t + 1, pairs of equal values every even one."""
+    from statistics import NormalDist
+
+    nd = NormalDist()
+    rng = np.random.default_rng(m)
+    perm = rng.permutation(m).astype(np.float64)
+    pairs = np.repeat(np.arange(m // 2, dtype=np.float64), 2)[rng.permutation(m)]
+    r = B.ranks_batch(np.stack([perm, pairs]).reshape(2, 1, m), folded=False)
+    z = r["z"].cpu().numpy().reshape(2, m)
+    rank = r["avg_rank"].cpu().numpy().reshape(2, m)
+    assert np.array_equal(rank[0], perm + 1.0) and np.array_equal(rank[1], 2.0 * pairs + 1.5)
+    want_odd = np.array([nd.inv_cdf((t + 0.5) / m) for t in range(m)])          # untied draw at sorted position t
+    want_even = np.array([nd.inv_cdf((2 * j + 1.0) / m) for j in range(m // 2)])  # run [2j, 2j + 2): k = 4j + 2
+    assert np.array_equal(z[0], want_odd[perm.astype(np.int64)])
+    assert np.array_equal(z[1], want_even[pairs.astype(np.int64)])
+
+
+def test_numpy_layout_rows_param_fastest(B):
+    """`Draws.to_numpy()` layout ([C * N, P], parameter fastest, draws.py:20-29) through the transposing load:
+    the same bits as the canonical [P, C, N] tensor -- odd P, ragged tile edges, and a workspace that forces
+    several parameter blocks."""
+    rng = np.random.default_rng(23)
+    for p, c, n in ((37, 4, 1001), (5, 6, 333), (64, 4, 2048)):
+        x = rng.standard_normal((p, c, n)) * rng.uniform(0.5, 2.0, (p, 1, 1)) + rng.integers(-3, 3, (p, 1, 1))
+        x[p // 2] = np.round(x[p // 2], 1)  # a tied parameter
+        rows = np.ascontiguousarray(x.reshape(p, c * n).T)  # [C * N, P]
+        want = B.diagnostics_batch(x)
+        got = B.diagnostics_rows(rows, n_chains=c)
+        for k, v in want.items():
+            assert np.array_equal(v.cpu().numpy(), got[k].cpu().numpy(), equal_nan=True), (p, c, n, k)
+    with pytest.raises(ValueError, match="equal chains"):
+        B.diagnostics_rows(np.zeros((10, 3)), n_chains=4)

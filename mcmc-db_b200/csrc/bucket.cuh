@@ -112,6 +112,16 @@ __device__ __forceinline__ int fine_of(double x, double L, double fs) {
   return (t >= 0.0) ? ((t < (double)NFINE) ? (int)t : NFINE - 1) : 0;
 }
 
+// A value repeated so often that it fills whole coarse buckets shows up as DUPLICATE splitters.  k_sample moves
+// the last duplicate one ulp up, which makes the coarse bucket [v, nextafter(v)) hold the copies of v and nothing
+// else: a "pure" bucket.  Its draws need no ranking -- they all share the run [B0, B0 + n) -- so it may have any
+// size: k_finish streams it through, and it never sends its parameter to the oversize list or the LSD path.
+// (Discrete and zero-inflated columns are normal in real posteriors.)
+__device__ __forceinline__ bool coarse_is_pure(const double* sp, int nb1, int c) {
+  if (c < 1 || c > nb1 - 2) return false;
+  return dbl2key(sp[c]) == dbl2key(sp[c - 1]) + 1ull;
+}
+
 struct BucketBufs {
   BucketFn* fn;        // [PB]
   uint32_t* cnt;       // [PB][nchunks][NB1_MAX]  per-chunk bucket counts -> exclusive offsets
@@ -143,10 +153,13 @@ struct BucketBufs {
 __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, uint32_t M, BucketBufs b) {
   __shared__ uint64_t s[NB1_MAX * OVERSAMPLE];
   __shared__ int scell[NB1_MAX];
+  __shared__ double spfix[NB1_MAX];
+  __shared__ uint8_t fixed[NB1_MAX];
   const int p = blockIdx.x;
   const double* xp = x + (size_t)p * M;
   BucketFn* fn = b.fn + p;
   const int nb1 = choose_nb1(M);
+  for (int j = threadIdx.x; j < NB1_MAX; j += 512) fixed[j] = 0;
   const uint32_t S = min((uint32_t)(nb1 * OVERSAMPLE), M);  // samples actually taken
   uint32_t S2 = 1;
   while (S2 < S) S2 <<= 1;                                   // padded to a power of two
@@ -200,6 +213,18 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     fn->sp[j] = v;
     scell[j] = c;
   }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nb1 - 1; j += 512) {
+    // last of a group of equal splitters -> one ulp up: the bucket below it becomes pure (see coarse_is_pure)
+    const double v = fn->sp[j];
+    if (j >= 1 && fn->sp[j - 1] == v && (j == nb1 - 2 || fn->sp[j + 1] != v)) {
+      const double up1 = key2dbl(dbl2key(v) + 1ull);
+      if (is_finite_bits(up1)) { spfix[j] = up1; fixed[j] = 1; }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nb1 - 1; j += 512)
+    if (fixed[j]) { fn->sp[j] = spfix[j]; scell[j] = cell_of(spfix[j], lo, csf); }
   __syncthreads();
   for (int j = threadIdx.x; j < NB1_MAX; j += 512) {
     // scale of the sub-bucket / fine-bucket function of coarse bucket j
@@ -315,7 +340,10 @@ __global__ void __launch_bounds__(NB1_MAX) k_bscan(uint32_t M, uint32_t nchunks,
       run += v[j];
     }
   }
-  if (run > (uint32_t)CAPBIG) {
+  const bool pure = coarse_is_pure(b.fn[p].sp, b.fn[p].nb1, t);
+  if (pure) {
+    // any size: k_finish streams it
+  } else if (run > (uint32_t)CAPBIG) {
     over = 1;
   } else if (run > (uint32_t)CAP1) {
     const int slot = atomicAdd(b.nbigb, 1);
@@ -838,13 +866,16 @@ __global__ void __launch_bounds__(BSW_NT) k_bscan_w(uint32_t M, uint32_t nchunks
   __syncthreads();
   uint32_t* cur = b.cur + (size_t)p * NBW_MAX;
   const int nbt = b.fn[p].nb1 * b.fn[p].sub;
+  const int wsh = 31 - __clz(b.fn[p].sub);  // sub is a power of two
   uint32_t c[PER], tsum = 0;
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int i = t * PER + k;
     c[k] = (i < nbt) ? cur[i] : 0u;
     tsum += c[k];
-    if (c[k] > (uint32_t)CAPBIG) {
+    if (c[k] > (uint32_t)CAP1 && coarse_is_pure(b.fn[p].sp, b.fn[p].nb1, i >> wsh)) {
+      // pure coarse bucket (all of it in its sub-bucket 0): any size, k_finish streams it
+    } else if (c[k] > (uint32_t)CAPBIG) {
       over = 1;
     } else if (c[k] > (uint32_t)CAP1) {
       const int slot = atomicAdd(b.nbigb, 1);
@@ -1029,7 +1060,22 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
       for (int i = 0; i < 2 * 8 + 2; ++i)  // static indices: the parameter struct stays in the constant bank
         wanted |= (i < fo.npos) && (fo.pos[i] - B0 < n);  // unsigned: B0 <= pos < B0 + n
     }
-    if (wanted && n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
+    if (wanted && n > (uint32_t)FIN_NT && coarse_is_pure(fn->sp, fn->nb1, cb >> sh)) {
+      // copies of one value (see coarse_is_pure): one tie run [B0, B0 + n), nothing to rank.  (Small pure
+      // buckets take the general path below, which handles them just as well.)
+      const uint32_t kc = 2u * B0 + n;
+      uint64_t* ok = b.skey + (size_t)p * M + B0;
+      uint32_t* oi = b.sidx + (size_t)p * M + B0;
+      uint32_t* oc = b.kcode + (size_t)p * M + B0;
+      double* orank = fo.rank ? fo.rank + (size_t)p * M : nullptr;
+      for (uint32_t e = tid; e < n; e += FIN_NT) {
+        const uint32_t pos = pi0[B0 + e];
+        ok[e] = pk0[B0 + e];
+        oi[e] = pos | TIED_BIT;
+        oc[e] = kc;
+        if (orank) orank[pos] = (double)(kc + 1u) * 0.5;
+      }
+    } else if (wanted && n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
         finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false, false>(sm, ff, B0, n, M, p, b, fo);
       __syncthreads();
     }

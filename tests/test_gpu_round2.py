@@ -253,3 +253,48 @@ def test_numpy_layout_rows_param_fastest(B):
             assert np.array_equal(v.cpu().numpy(), got[k].cpu().numpy(), equal_nan=True), (p, c, n, k)
     with pytest.raises(ValueError, match="equal chains"):
         B.diagnostics_rows(np.zeros((10, 3)), n_chains=4)
+
+
+def test_heavy_ties_stay_on_the_fast_path(B):
+    """Zero-inflated and discrete columns (normal in real posteriors): a value repeated far more often than any
+    on-chip bucket holds gets a coarse bucket of its own (duplicate splitters -> [v, nextafter(v))) and is
+    streamed, not sorted.  Exact ranks / scores / diagnostics, and no single-CTA LSD fallback: the pass over
+    such columns costs about what it costs over continuous ones."""
+    import time
+
+    import torch
+
+    rng = np.random.default_rng(41)
+    c, n = 16, 10_000
+    cont = rng.standard_normal((c, n))
+    half_zero = np.where(rng.random((c, n)) < 0.5, 0.0, cont)
+    spike = np.where(rng.random((c, n)) < 0.3, 1.25, cont) + np.where(rng.random((c, n)) < 0.1, -0.0, 0.0)
+    for name, x in (("half_zero", half_zero), ("spike_030", spike)):
+        m = x.size
+        r = B.ranks_batch(x[None])
+        rank, z = O.rank_normalize(x)
+        rank_f, z_f = O.rank_normalize(O.fold_chains(x))
+        assert np.array_equal(r["avg_rank"][0].cpu().numpy(), rank), name
+        assert np.array_equal(r["avg_rank_folded"][0].cpu().numpy(), rank_f), name
+        assert np.array_equal(r["z"][0].cpu().numpy(), z) and np.array_equal(r["z_folded"][0].cpu().numpy(), z_f), name
+        _check_vs_oracle(B, x, name)
+    # 21 equally likely values at the config-5 size: each holds more draws than the largest on-chip bucket
+    disc = rng.integers(0, 21, (64, 4096)).astype(np.float64) * 0.5 - 3.0
+    _check_vs_oracle(B, disc, "discrete_21")
+    # cost: 64 zero-inflated columns against 64 continuous ones (same shape), best of 3
+    xs = {"cont": rng.standard_normal((64, c, n)), "half_zero": None}
+    xs["half_zero"] = np.where(rng.random((64, c, n)) < 0.5, 0.0, xs["cont"])
+    ms = {}
+    for name, x in xs.items():
+        xt = B.to_device(x)
+        B.diagnostics_batch(xt)
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            B.diagnostics_batch(xt)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        ms[name] = best * 1e3
+    print(f"heavy ties: continuous {ms['cont']:.2f} ms, 50 % zeros {ms['half_zero']:.2f} ms")
+    assert ms["half_zero"] < 3.0 * ms["cont"], ms

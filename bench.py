@@ -319,7 +319,8 @@ def glm_measure(args, rank: int, world: int, local: int, full: bool) -> dict:
     steps = args.steps if full else min(args.steps, 10)
 
     def step():
-        return logdensity.glm_lp_sharded("bernoulli_logit", X, y, beta_local, n_draws=s, workspace=ws)
+        # the design is the same device tensor every step: its staged bf16 split is reused (the first call stages it)
+        return logdensity.glm_lp_sharded("bernoulli_logit", X, y, beta_local, n_draws=s, workspace=ws, reuse_design=True)
 
     def barrier():
         if world > 1:

@@ -7,8 +7,10 @@
 // tcgen05 design (sm_100a):
 //   * the contraction eta[S x N] = beta[S x D] * X[N x D]^T runs on the 5th-gen tensor cores;
 //     fp64 inputs are split into bf16 hi + lo parts (16 significant bits) and three MMAs
-//     (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM -- |d eta| ~ 1e-5, which moves lp by
-//     < 1e-7 relative because the errors average out over the N terms;
+//     (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM.  Only the draws' DEVIATIONS from their mean are
+//     contracted (eta = X mean(beta) + X (beta_s - mean(beta)); the first part is one fp64 matrix-vector product
+//     per call, added back in the epilogue), so the 2^-16 relative error of the split scales with the spread
+//     of the draws, not with eta: lp agrees with fp64 to ~1e-7 relative for posterior-like draws;
 //   * UMMA tile 128 draws x 256 data rows x K 16, cta_group::1; DRAWS are the M dimension so
 //     that every TMEM lane (= one epilogue thread) owns one draw and can keep a private
 //     running sum over data rows -- no cross-thread reduction in the epilogue;
@@ -39,7 +41,7 @@ constexpr int GLM_EPI_THREADS = 256;
 constexpr uint32_t GLM_A_BYTES = GLM_BM * GLM_BK * 2;  // 16 KB
 constexpr uint32_t GLM_B_BYTES = GLM_BN * GLM_BK * 2;  // 32 KB
 constexpr uint32_t GLM_STAGE_BYTES = 2 * GLM_A_BYTES + 2 * GLM_B_BYTES;  // 96 KB
-constexpr size_t GLM_SMEM_BYTES = 1024 + (size_t)GLM_STAGES * GLM_STAGE_BYTES + 4 * GLM_BN * 4 + 256;
+constexpr size_t GLM_SMEM_BYTES = 1024 + (size_t)GLM_STAGES * GLM_STAGE_BYTES + 6 * GLM_BN * 4 + 256;
 
 // Likelihood families (Stan `~` semantics: terms that do not depend on the parameters are dropped):
 //   0 bernoulli_logit  sum_n y eta - softplus(eta)
@@ -56,6 +58,9 @@ struct GlmParams {
   int nsplit;          // row-tile slices per draw tile
   const float* yf;     // [n_row_tiles * 256] y as float, padded with 0
   const float* af;     // [n_row_tiles * 256] binomial trials as float (binomial_logit), else unused
+  const float* of;     // [n_row_tiles * 256] eta of the MEAN draw per data row (X * mean(beta), evaluated in fp64):
+                       // the tensor cores contract only the draws' deviations from their mean, the epilogue adds
+                       // this offset back -- the split-bf16 error then scales with the deviations, not with eta
   double* lp_part;     // [nsplit][S], zero-initialised
 };
 
@@ -112,18 +117,41 @@ constexpr uint32_t GLM_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(
                                ((uint32_t)(GLM_BM >> 4) << 24);
 
 // ---- helper kernels -------------------------------------------------------------------------
-// fp64 [rows][D] -> bf16 hi, lo [rows][Dpad] (zero padded): x ~ hi + lo with 16 significant bits
-__global__ void k_glm_split(const double* __restrict__ src, int64_t rows, int D, int Dpad, __nv_bfloat16* __restrict__ hi,
-                            __nv_bfloat16* __restrict__ lo) {
+// fp64 [rows][D] (minus an optional per-column centre) -> bf16 hi, lo [rows][Dpad] (zero padded):
+// x ~ hi + lo with 16 significant bits
+__global__ void k_glm_split(const double* __restrict__ src, const double* __restrict__ center, int64_t rows, int D, int Dpad,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * Dpad) return;
   const int64_t r = i / Dpad;
   const int d = (int)(i % Dpad);
   double x = (d < D) ? src[r * D + d] : 0.0;
+  if (center && d < D) x -= center[d];
   const __nv_bfloat16 h = __double2bfloat16(x);
   const double rem = x - (double)__bfloat162float(h);
   hi[i] = h;
   lo[i] = __double2bfloat16(rem);
+}
+// mean draw: center[d] = mean_s beta[s][d]  (one CTA per column, fixed reduction tree: deterministic)
+__global__ void __launch_bounds__(256) k_glm_center(const double* __restrict__ beta, int64_t S, int D, double* __restrict__ center) {
+  __shared__ double red[33];
+  const int d = blockIdx.x;
+  double a = 0.0;
+  for (int64_t s = threadIdx.x; s < S; s += 256) a += beta[s * D + d];
+  a = block_sum<256>(a, red);
+  if (threadIdx.x == 0) center[d] = a / (double)S;
+}
+// eta of the mean draw per data row, in fp64, stored as float (padding rows 0): one warp per row
+__global__ void __launch_bounds__(256) k_glm_offset(const double* __restrict__ X, const double* __restrict__ center, int64_t N,
+                                                    int D, int64_t Npad, float* __restrict__ of) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= Npad) return;
+  double a = 0.0;
+  if (row < N)
+    for (int d = lane; d < D; d += 32) a = fma(X[row * D + d], center[d], a);
+  a = warp_sum(a);
+  if (lane == 0) of[row] = (float)a;
 }
 __global__ void k_glm_y(const double* __restrict__ y, int64_t N, int64_t Npad, float* __restrict__ yf) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,7 +181,8 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
   unsigned char* stage_base = smem;
   float* ys = (float*)(smem + (size_t)GLM_STAGES * GLM_STAGE_BYTES);  // [2][256] y, then [2][256] trials
   float* as = ys + 2 * GLM_BN;
-  uint64_t* bars = (uint64_t*)(ys + 4 * GLM_BN);
+  float* os = ys + 4 * GLM_BN;                                         // [2][256] offsets (eta of the mean draw)
+  uint64_t* bars = (uint64_t*)(ys + 6 * GLM_BN);
   uint64_t* full = bars;            // [2]  TMA -> MMA
   uint64_t* empty = bars + 2;       // [2]  MMA -> TMA
   uint64_t* tfull = bars + 4;       // [2]  MMA -> epilogue
@@ -253,12 +282,14 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
         // stage y for this tile's 256 data rows (one element per epilogue thread)
         ys[abuf * GLM_BN + et] = prm.yf[(size_t)rt * GLM_BN + et];
         if (FAM == GLM_BINOMIAL_LOGIT) as[abuf * GLM_BN + et] = prm.af[(size_t)rt * GLM_BN + et];
+        os[abuf * GLM_BN + et] = prm.of[(size_t)rt * GLM_BN + et];
         mbar_wait(&tfull[abuf], aphase);
         tc_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(GLM_EPI_THREADS) : "memory");
         const int64_t nvalid = prm.N - (int64_t)rt * GLM_BN;  // rows of this tile that exist
         const float* yt = ys + abuf * GLM_BN;
         const float* at = as + abuf * GLM_BN;
+        const float* ot = os + abuf * GLM_BN;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int col0 = chalf * 128 + cc * 32;
@@ -267,7 +298,7 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
           float part = 0.0f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float eta = __uint_as_float(v[j]);
+            const float eta = __uint_as_float(v[j]) + ot[col0 + j];  // deviation part (tensor cores) + mean-draw part
             float term;
             if (FAM == GLM_BERNOULLI_LOGIT || FAM == GLM_BINOMIAL_LOGIT) {
               const float a = fabsf(eta);

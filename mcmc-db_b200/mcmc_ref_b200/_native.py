@@ -26,10 +26,11 @@ EXPORTS = (
     "b200ref_ranks_f64", "b200ref_diagnostics_f64", "b200ref_diagnostics_ex_f64", "b200ref_stats_f64",
     "b200ref_compare_f64", "b200ref_checks_f64",
     "b200ref_full_pass_workspace_bytes", "b200ref_full_pass_f64", "b200ref_full_pass_host_f64", "b200ref_synth_fill_f64",
-    "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64", "b200ref_glm_lp_f64",
+    "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64", "b200ref_glm_lp_f64", "b200ref_glm_lp_ex_f64",
     "b200ref_row_order_i64", "b200ref_gather_rows_f64",
     "b200ref_rows_workspace_bytes", "b200ref_diagnostics_layout_f64", "b200ref_transpose_rows_f64",
 )
+GLM_REUSE_DESIGN = 1
 LAYOUTS = {"pcn": 0, "rows": 1}
 
 
@@ -91,6 +92,7 @@ def load() -> C.CDLL:
     lib.b200ref_glm_workspace_bytes.argtypes = [i64, i64, i64]
     lib.b200ref_glm_logistic_lp_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, sz, vp]
     lib.b200ref_glm_lp_f64.argtypes = [C.c_int, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, sz, vp]
+    lib.b200ref_glm_lp_ex_f64.argtypes = [C.c_int, vp, vp, vp, vp, vp, i64, i64, i64, C.c_int, vp, vp, sz, vp]
     lib.b200ref_row_order_i64.argtypes = [vp, vp, i64, C.POINTER(C.c_int), vp]
     lib.b200ref_gather_rows_f64.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.b200ref_rows_workspace_bytes.restype = sz

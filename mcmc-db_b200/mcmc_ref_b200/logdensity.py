@@ -31,7 +31,8 @@ def logistic_lp(X, y, beta, workspace: batch.Workspace | None = None) -> torch.T
     return lp
 
 
-def glm_lp(family: str, X, y, beta, trials=None, sigma=None, workspace: batch.Workspace | None = None) -> torch.Tensor:
+def glm_lp(family: str, X, y, beta, trials=None, sigma=None, workspace: batch.Workspace | None = None,
+           reuse_design: bool = False) -> torch.Tensor:
     """lp[S] of the likelihood block of a packaged GLM-style model, eta = X @ beta[s] (Stan ``~`` semantics:
     parameter-free terms dropped):
 
@@ -39,6 +40,9 @@ def glm_lp(family: str, X, y, beta, trials=None, sigma=None, workspace: batch.Wo
     * ``"binomial_logit"``   ``y ~ binomial_logit(trials, X * beta)``   (provenance.py:567-606)
     * ``"poisson_log"``      ``y ~ poisson_log(X * beta)``              (provenance.py:609-640)
     * ``"normal"``           ``y ~ normal(X * beta, sigma)``, ``sigma`` [S] per draw (sblri-blr.stan:12-17)
+
+    ``reuse_design=True``: the caller states that ``X`` / ``y`` / ``trials`` are the SAME device tensors as in the
+    previous call with this workspace (new draws against the same design); the staged bf16 split of X is reused.
     """
     if family not in _native.GLM_FAMILIES:
         raise ValueError(f"family must be one of {sorted(_native.GLM_FAMILIES)}; got {family!r}")
@@ -63,22 +67,24 @@ def glm_lp(family: str, X, y, beta, trials=None, sigma=None, workspace: batch.Wo
             raise ValueError(f"shape mismatch: sigma {tuple(st.shape)} for S = {s}")
     lp = torch.empty(s, dtype=torch.float64, device=xt.device)
     ws = (workspace or _WS).ensure(int(lib.b200ref_glm_workspace_bytes(n, d, s)))
-    _native.check(lib.b200ref_glm_lp_f64(_native.GLM_FAMILIES[family], xt.data_ptr(), yt.data_ptr(),
-                                         tt.data_ptr() if tt is not None else None, bt.data_ptr(),
-                                         st.data_ptr() if st is not None else None, n, d, s, lp.data_ptr(),
-                                         ws.data_ptr(), ws.numel(), batch._stream_ptr()))
+    flags = _native.GLM_REUSE_DESIGN if reuse_design else 0
+    _native.check(lib.b200ref_glm_lp_ex_f64(_native.GLM_FAMILIES[family], xt.data_ptr(), yt.data_ptr(),
+                                            tt.data_ptr() if tt is not None else None, bt.data_ptr(),
+                                            st.data_ptr() if st is not None else None, n, d, s, flags, lp.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), batch._stream_ptr()))
     return lp
 
 
 def glm_lp_sharded(family: str, X, y, beta_local, n_draws: int | None = None, trials=None, sigma_local=None,
-                   group=None, workspace: batch.Workspace | None = None) -> torch.Tensor:
+                   group=None, workspace: batch.Workspace | None = None, reuse_design: bool = False) -> torch.Tensor:
     """Draw-block sharded ``glm_lp``: every rank holds the design ``X`` / ``y`` (replicated once,
     see ``broadcast_design``) and ITS contiguous block of the draws (``sharding.shard_bounds(n_draws, world, rank)``;
     ``sigma_local`` likewise for the normal family); each evaluates its block on its own GPU and one all_gather
     of the S log-densities gives every rank ``lp[S]`` in draw order.  Single process: same as ``glm_lp``."""
     from . import sharding
 
-    lp_local = glm_lp(family, X, y, beta_local, trials=trials, sigma=sigma_local, workspace=workspace)
+    lp_local = glm_lp(family, X, y, beta_local, trials=trials, sigma=sigma_local, workspace=workspace,
+                      reuse_design=reuse_design)
     return sharding.gather_draw_blocks(lp_local, n_draws, group)
 
 

@@ -1073,7 +1073,7 @@ struct GlmStaged {
 constexpr uint64_t GLM_MAGIC = 0xb200f00dd5a17e55ull;
 
 struct GlmLayout {
-  size_t bh, bl, xh, xl, yf, af, of, center, part, hdr, total;
+  size_t bh, bl, xh, xl, yf, af, center, part, hdr, total;
   int Dpad, n_row_tiles, n_draw_tiles, nsplit;
   void compute(int64_t N, int64_t D, int64_t S) {
     Dpad = (int)((D + GLM_BK - 1) / GLM_BK * GLM_BK);
@@ -1087,7 +1087,6 @@ struct GlmLayout {
     xl = o; o += up((size_t)N * Dpad * 2);
     yf = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
     af = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
-    of = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
     center = o; o += up((size_t)Dpad * 8);
     part = o; o += up((size_t)nsplit * S * 8);
     hdr = o; o += up(sizeof(GlmStaged));
@@ -1131,7 +1130,6 @@ int b200ref_glm_lp_ex_f64(int family, const double* X, const double* y, const do
   float* yf = (float*)(w + L.yf);
   float* af = (float*)(w + L.af);
   double* part = (double*)(w + L.part);
-  float* of = (float*)(w + L.of);
   double* center = (double*)(w + L.center);
   const int64_t nb = S * L.Dpad, nx = N * L.Dpad, npad = (int64_t)L.n_row_tiles * GLM_BN;
   // the design's staged copies (bf16 split of X, float y / trials) are reused when the caller says this call's
@@ -1144,15 +1142,22 @@ int b200ref_glm_lp_ex_f64(int family, const double* X, const double* y, const do
     CUDA_TRY(cudaStreamSynchronize(st));
     reuse = memcmp(&have, &want, sizeof(have)) == 0;
   }
-  // the mean draw and its linear predictor in fp64; the tensor cores see only the deviations beta_s - mean
-  LAUNCH(K_GLM_PREP, st, k_glm_center<<<(unsigned)D, 256, 0, st>>>(beta, S, (int)D, center));
-  LAUNCH(K_GLM_PREP, st, k_glm_offset<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(X, center, N, (int)D, npad, of));
-  LAUNCH(K_GLM_PREP, st, k_glm_split<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(beta, center, S, (int)D, L.Dpad, bh, bl));
-  if (!reuse) {
+  // normal family: the squared residual amplifies the error of the split-bf16 contraction, so only the draws'
+  // deviations from their mean are contracted and the mean draw's predictor (fp64) is folded into the response
+  const bool centered = family == GLM_NORMAL;
+  if (centered) LAUNCH(K_GLM_PREP, st, k_glm_center<<<(unsigned)D, 256, 0, st>>>(beta, S, (int)D, center));
+  LAUNCH(K_GLM_PREP, st, k_glm_split<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(beta, centered ? center : nullptr, S, (int)D, L.Dpad, bh, bl));
+  if (!reuse)
     LAUNCH(K_GLM_PREP, st, k_glm_split<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(X, nullptr, N, (int)D, L.Dpad, xh, xl));
+  if (centered) {
+    LAUNCH(K_GLM_PREP, st, k_glm_y_centered<<<(unsigned)((npad + 7) / 8), 256, 0, st>>>(y, X, center, N, (int)D, npad, yf));
+  } else if (!reuse) {
     LAUNCH(K_GLM_PREP, st, k_glm_y<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(y, N, npad, yf));
     if (family == GLM_BINOMIAL_LOGIT)
       LAUNCH(K_GLM_PREP, st, k_glm_y<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(trials, N, npad, af));
+  }
+  if (!reuse) {
+    want.y = centered ? nullptr : y;  // the staged response of a centred call depends on the draws: never reused
     CUDA_TRY(cudaMemcpyAsync(w + L.hdr, &want, sizeof(want), cudaMemcpyHostToDevice, st));
   }
   CUDA_TRY(cudaMemsetAsync(part, 0, (size_t)L.nsplit * S * 8, st));
@@ -1165,7 +1170,7 @@ int b200ref_glm_lp_ex_f64(int family, const double* X, const double* y, const do
   GlmParams prm;
   prm.N = N; prm.S = S; prm.Dpad = L.Dpad;
   prm.n_row_tiles = L.n_row_tiles; prm.n_draw_tiles = L.n_draw_tiles; prm.nsplit = L.nsplit;
-  prm.yf = yf; prm.af = af; prm.of = of; prm.lp_part = part;
+  prm.yf = yf; prm.af = af; prm.lp_part = part;
   static bool attr_dev[MAX_DEVICES] = {};
   bool& attr = attr_dev[current_device()];
   if (!attr) {

@@ -7,10 +7,12 @@
 // tcgen05 design (sm_100a):
 //   * the contraction eta[S x N] = beta[S x D] * X[N x D]^T runs on the 5th-gen tensor cores;
 //     fp64 inputs are split into bf16 hi + lo parts (16 significant bits) and three MMAs
-//     (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM.  Only the draws' DEVIATIONS from their mean are
-//     contracted (eta = X mean(beta) + X (beta_s - mean(beta)); the first part is one fp64 matrix-vector product
-//     per call, added back in the epilogue), so the 2^-16 relative error of the split scales with the spread
-//     of the draws, not with eta: lp agrees with fp64 to ~1e-7 relative for posterior-like draws;
+//     (hi*hi + hi*lo + lo*hi) accumulate in fp32 in TMEM -- |d eta| ~ 1e-5 |eta|, which moves lp by
+//     < 1e-7 relative because the errors average out over the N terms.  The NORMAL family squares the
+//     residual y - eta, which amplifies d eta by |eta| / |y - eta|: there only the draws' DEVIATIONS from their
+//     mean are contracted (y - X beta_s = (y - X mean(beta)) - X (beta_s - mean(beta)); the first bracket is one
+//     fp64 matrix-vector product per call, folded into the response) -- exact algebra, no epilogue cost, and the
+//     error of the split then scales with the spread of the draws instead of with eta;
 //   * UMMA tile 128 draws x 256 data rows x K 16, cta_group::1; DRAWS are the M dimension so
 //     that every TMEM lane (= one epilogue thread) owns one draw and can keep a private
 //     running sum over data rows -- no cross-thread reduction in the epilogue;
@@ -41,7 +43,7 @@ constexpr int GLM_EPI_THREADS = 256;
 constexpr uint32_t GLM_A_BYTES = GLM_BM * GLM_BK * 2;  // 16 KB
 constexpr uint32_t GLM_B_BYTES = GLM_BN * GLM_BK * 2;  // 32 KB
 constexpr uint32_t GLM_STAGE_BYTES = 2 * GLM_A_BYTES + 2 * GLM_B_BYTES;  // 96 KB
-constexpr size_t GLM_SMEM_BYTES = 1024 + (size_t)GLM_STAGES * GLM_STAGE_BYTES + 6 * GLM_BN * 4 + 256;
+constexpr size_t GLM_SMEM_BYTES = 1024 + (size_t)GLM_STAGES * GLM_STAGE_BYTES + 4 * GLM_BN * 4 + 256;
 
 // Likelihood families (Stan `~` semantics: terms that do not depend on the parameters are dropped):
 //   0 bernoulli_logit  sum_n y eta - softplus(eta)
@@ -58,9 +60,6 @@ struct GlmParams {
   int nsplit;          // row-tile slices per draw tile
   const float* yf;     // [n_row_tiles * 256] y as float, padded with 0
   const float* af;     // [n_row_tiles * 256] binomial trials as float (binomial_logit), else unused
-  const float* of;     // [n_row_tiles * 256] eta of the MEAN draw per data row (X * mean(beta), evaluated in fp64):
-                       // the tensor cores contract only the draws' deviations from their mean, the epilogue adds
-                       // this offset back -- the split-bf16 error then scales with the deviations, not with eta
   double* lp_part;     // [nsplit][S], zero-initialised
 };
 
@@ -98,6 +97,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
 }
 
 // K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart):
@@ -141,9 +146,10 @@ __global__ void __launch_bounds__(256) k_glm_center(const double* __restrict__ b
   a = block_sum<256>(a, red);
   if (threadIdx.x == 0) center[d] = a / (double)S;
 }
-// eta of the mean draw per data row, in fp64, stored as float (padding rows 0): one warp per row
-__global__ void __launch_bounds__(256) k_glm_offset(const double* __restrict__ X, const double* __restrict__ center, int64_t N,
-                                                    int D, int64_t Npad, float* __restrict__ of) {
+// response minus the linear predictor of the mean draw, in fp64, stored as float (padding rows 0): one warp per row
+__global__ void __launch_bounds__(256) k_glm_y_centered(const double* __restrict__ y, const double* __restrict__ X,
+                                                        const double* __restrict__ center, int64_t N, int D, int64_t Npad,
+                                                        float* __restrict__ yf) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= Npad) return;
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(256) k_glm_offset(const double* __restrict__ X
   if (row < N)
     for (int d = lane; d < D; d += 32) a = fma(X[row * D + d], center[d], a);
   a = warp_sum(a);
-  if (lane == 0) of[row] = (float)a;
+  if (lane == 0) yf[row] = (row < N) ? (float)(y[row] - a) : 0.0f;
 }
 __global__ void k_glm_y(const double* __restrict__ y, int64_t N, int64_t Npad, float* __restrict__ yf) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,8 +187,7 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
   unsigned char* stage_base = smem;
   float* ys = (float*)(smem + (size_t)GLM_STAGES * GLM_STAGE_BYTES);  // [2][256] y, then [2][256] trials
   float* as = ys + 2 * GLM_BN;
-  float* os = ys + 4 * GLM_BN;                                         // [2][256] offsets (eta of the mean draw)
-  uint64_t* bars = (uint64_t*)(ys + 6 * GLM_BN);
+  uint64_t* bars = (uint64_t*)(ys + 4 * GLM_BN);
   uint64_t* full = bars;            // [2]  TMA -> MMA
   uint64_t* empty = bars + 2;       // [2]  MMA -> TMA
   uint64_t* tfull = bars + 4;       // [2]  MMA -> epilogue
@@ -282,14 +287,14 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
         // stage y for this tile's 256 data rows (one element per epilogue thread)
         ys[abuf * GLM_BN + et] = prm.yf[(size_t)rt * GLM_BN + et];
         if (FAM == GLM_BINOMIAL_LOGIT) as[abuf * GLM_BN + et] = prm.af[(size_t)rt * GLM_BN + et];
-        os[abuf * GLM_BN + et] = prm.of[(size_t)rt * GLM_BN + et];
         mbar_wait(&tfull[abuf], aphase);
         tc_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(GLM_EPI_THREADS) : "memory");
         const int64_t nvalid = prm.N - (int64_t)rt * GLM_BN;  // rows of this tile that exist
-        const float* yt = ys + abuf * GLM_BN;
-        const float* at = as + abuf * GLM_BN;
-        const float* ot = os + abuf * GLM_BN;
+        // y and the binomial trials of the tile's data rows, 4 rows per LDS.128 broadcast.  (explicit ld.shared: the
+        // 1 KB round-up of the dynamic shared-memory base goes through an integer, after which the compiler only
+        // knows a generic pointer and emits LD.E instead of LDS)
+        const uint32_t yt4 = smem_u32(ys + abuf * GLM_BN), at4 = smem_u32(as + abuf * GLM_BN);
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int col0 = chalf * 128 + cc * 32;
@@ -297,26 +302,34 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
           tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(abuf * GLM_BN + col0), v);
           float part = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float eta = __uint_as_float(v[j]) + ot[col0 + j];  // deviation part (tensor cores) + mean-draw part
-            float term;
-            if (FAM == GLM_BERNOULLI_LOGIT || FAM == GLM_BINOMIAL_LOGIT) {
-              const float a = fabsf(eta);
-              float e, l;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * LOG2E));
-              asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-              const float sp = fmaxf(eta, 0.0f) + l * LN2;  // softplus
-              term = yt[col0 + j] * eta - ((FAM == GLM_BINOMIAL_LOGIT) ? at[col0 + j] * sp : sp);
-            } else if (FAM == GLM_POISSON_LOG) {
-              float e;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(eta * LOG2E));
-              term = yt[col0 + j] * eta - e;
-            } else {
-              const float r = yt[col0 + j] - eta;
-              term = -r * r;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 y4 = lds128(yt4 + (uint32_t)(col0 + 4 * j4) * 4u);
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FAM == GLM_BINOMIAL_LOGIT) a4 = lds128(at4 + (uint32_t)(col0 + 4 * j4) * 4u);
+            const float yy[4] = {y4.x, y4.y, y4.z, y4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int j = 4 * j4 + q;
+              const float eta = __uint_as_float(v[j]);
+              float term;
+              if (FAM == GLM_BERNOULLI_LOGIT || FAM == GLM_BINOMIAL_LOGIT) {
+                const float a = fabsf(eta);
+                float e, l;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * LOG2E));
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+                const float sp = fmaxf(eta, 0.0f) + l * LN2;  // softplus
+                term = yy[q] * eta - ((FAM == GLM_BINOMIAL_LOGIT) ? aa[q] * sp : sp);
+              } else if (FAM == GLM_POISSON_LOG) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(eta * LOG2E));
+                term = yy[q] * eta - e;
+              } else {
+                const float r = yy[q] - eta;
+                term = -r * r;
+              }
+              if (col0 + j >= nvalid) term = 0.0f;
+              part += term;
             }
-            if (col0 + j >= nvalid) term = 0.0f;
-            part += term;
           }
           acc += (double)part;
         }

@@ -1060,9 +1060,10 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
       for (int i = 0; i < 2 * 8 + 2; ++i)  // static indices: the parameter struct stays in the constant bank
         wanted |= (i < fo.npos) && (fo.pos[i] - B0 < n);  // unsigned: B0 <= pos < B0 + n
     }
-    if (wanted && n > (uint32_t)FIN_NT && coarse_is_pure(fn->sp, fn->nb1, cb >> sh)) {
-      // copies of one value (see coarse_is_pure): one tie run [B0, B0 + n), nothing to rank.  (Small pure
-      // buckets take the general path below, which handles them just as well.)
+    if (wanted && n > (uint32_t)CAP1 && coarse_is_pure(fn->sp, fn->nb1, cb >> sh)) {
+      // copies of one value (see coarse_is_pure): one tie run [B0, B0 + n), nothing to rank.  (Pure buckets that
+      // fit on-chip take the general path below, which handles them just as well: the purity test costs a
+      // dependent global read per bucket, so it is only made where it matters.)
       const uint32_t kc = 2u * B0 + n;
       uint64_t* ok = b.skey + (size_t)p * M + B0;
       uint32_t* oi = b.sidx + (size_t)p * M + B0;

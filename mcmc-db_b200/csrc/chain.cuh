@@ -384,19 +384,29 @@ struct MoR1Smem {
   double red[2][MO_NT / 32][LAGB];
 };
 
-__device__ __forceinline__ void moments_r1_unit(MoR1Smem& S, const double2* __restrict__ zc, const ChainGeom& g, uint32_t t0,
-                                                int kind, uint32_t u, double* __restrict__ out, uint64_t* bar, uint32_t& phase) {
+// One work unit of a later round, single-tile variant: sub-tiles [a, b) of the chain whose first pair is `zc`.
+struct R1Unit {
+  const double2* zc;
+  uint32_t a, b;   // a >= b: nothing to do (all first factors of the unit lie past N - t0)
+  int kind;
+  double* out;     // LAGR partial sums
+};
+
+// `staged`: this unit's first copy was already issued (by the previous unit of this CTA); `next`: the CTA's next
+// unit (or null) -- its first copy is issued as soon as this unit's last sub-tile has left the staging buffer, so
+// that only the first copy of a CTA's round is exposed.
+__device__ __forceinline__ void moments_r1_unit(MoR1Smem& S, const R1Unit& un, const ChainGeom& g, uint32_t t0, bool staged,
+                                                const R1Unit* next, uint64_t* bar, uint32_t& phase) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int hb = tid >> 7, ct = tid & (MO_NT - 1), wp = ct >> 5;  // hb: which block of 16 lags
-  uint32_t a, b;
-  unit_range(g, u, a, b);
-  const uint32_t lim = (g.N > t0) ? g.N - t0 : 0;  // first factors need i + t0 < N
-  b = min(b, lim);
+  const uint32_t a = un.a, b = un.b;
+  const int kind = un.kind;
+  const double2* zc = un.zc;
   const uint32_t span = MO_SUB + t0 + LAGR + CHUNK;  // pairs a full sub-tile touches
   double acc[LAGB];
 #pragma unroll
   for (int l = 0; l < LAGB; ++l) acc[l] = 0.0;
-  if (a < b && tid == 0) stage_pairs(S.raw, zc + a, min(span, g.N - a), bar);
+  if (a < b && !staged && tid == 0) stage_pairs(S.raw, zc + a, min(span, g.N - a), bar);
   const uint32_t goff = (t0 - 1) / CHUNK + (uint32_t)hb;  // group offset of the second-factor window
   for (uint32_t sub = a; sub < b; sub += MO_SUB) {
     const uint32_t len = min((uint32_t)MO_SUB, b - sub);
@@ -422,7 +432,10 @@ __device__ __forceinline__ void moments_r1_unit(MoR1Smem& S, const double2* __re
       }
     }
     __syncthreads();
-    if (tid == 0 && sub + MO_SUB < b) stage_pairs(S.raw, zc + sub + MO_SUB, min(span, g.N - (sub + MO_SUB)), bar);
+    if (tid == 0) {
+      if (sub + MO_SUB < b) stage_pairs(S.raw, zc + sub + MO_SUB, min(span, g.N - (sub + MO_SUB)), bar);
+      else if (next && next->a < next->b) stage_pairs(S.raw, next->zc + next->a, min(span, g.N - next->a), bar);
+    }
     const uint32_t i0 = ct * CHUNK;
     if (i0 < len) {
       const uint32_t nvalid = min((uint32_t)CHUNK, len - i0);
@@ -447,9 +460,9 @@ __device__ __forceinline__ void moments_r1_unit(MoR1Smem& S, const double2* __re
     double v = S.red[hb][0][ct];
 #pragma unroll
     for (int k = 1; k < MO_NT / 32; ++k) v += S.red[hb][k][ct];
-    out[hb * LAGB + ct] = v;
+    un.out[hb * LAGB + ct] = v;
   }
-  __syncthreads();  // S.red and the staging buffer are free for the CTA's next unit
+  __syncthreads();  // S.red is free for the CTA's next unit
 }
 
 constexpr int DEC_RED = LAGR + 2;
@@ -763,16 +776,41 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_ess_rounds(const double2* __restr
     const int nwork = __ldcg(&st.nwl[cur]);  // final since the barrier that ended the previous round
     if (nwork == 0) break;                   // uniform over the grid
     const uint64_t total = (uint64_t)nwork * upi;
-    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const uint32_t lim = (g.N > t0) ? g.N - t0 : 0;  // first factors need i + t0 < N
+    auto describe = [&](uint64_t w, R1Unit& un, uint32_t& u_out) {
       const int li = (int)(w / upi);
       const uint32_t cu = (uint32_t)(w - (uint64_t)li * upi);
       const uint32_t c = cu / g.nunits, u = cu - c * g.nunits;
       const int item = __ldcg(&st.wl[cur][li]);
-      const int p = item >> 1, kind = item & 1;
-      const double2* zc = zz + ((size_t)p * g.C + c) * g.N;
-      double* out = st.partr + (((size_t)li * g.C + c) * g.nunits + u) * LAGR;
-      if (t0 <= (uint32_t)MO_T0MAX) moments_r1_unit(S.m.r1, zc, g, t0, kind, u, out, &S.bar, phase);
-      else moments_r_unit(S.m.r, zc, g, t0, kind, u, out, &S.bar, phase);
+      un.zc = zz + ((size_t)(item >> 1) * g.C + c) * g.N;
+      un.kind = item & 1;
+      un.out = st.partr + (((size_t)li * g.C + c) * g.nunits + u) * LAGR;
+      unit_range(g, u, un.a, un.b);
+      un.b = min(un.b, lim);
+      u_out = u;
+    };
+    if (t0 <= (uint32_t)MO_T0MAX) {
+      // single-tile variant: the next unit's first copy is issued under the current unit's last sub-tile
+      R1Unit cu_, nx_;
+      uint32_t u_;
+      bool staged = false;
+      uint64_t w = blockIdx.x;
+      if (w < total) describe(w, cu_, u_);
+      for (; w < total; w += gridDim.x) {
+        const bool has_next = w + gridDim.x < total;
+        if (has_next) describe(w + gridDim.x, nx_, u_);
+        moments_r1_unit(S.m.r1, cu_, g, t0, staged, has_next ? &nx_ : nullptr, &S.bar, phase);
+        // the prefetch is issued from inside the sub-tile loop: only a unit that has sub-tiles can have issued it
+        staged = has_next && (cu_.a < cu_.b) && (nx_.a < nx_.b);
+        cu_ = nx_;
+      }
+    } else {
+      for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        R1Unit un;
+        uint32_t u;
+        describe(w, un, u);
+        moments_r_unit(S.m.r, un.zc, g, t0, un.kind, u, un.out, &S.bar, phase);
+      }
     }
     if (blockIdx.x == 0 && tid == 0) st.nwl[cur ^ 1] = 0;  // the list the decisions are about to build
     grid_barrier(gbar, target);

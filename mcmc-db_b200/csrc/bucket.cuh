@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const d
   for (uint32_t s = tid; s < n; s += PART_NT) {
     const uint32_t mm = sm.smeta[s];
     const uint32_t pos = sm.delta[mm >> 16] + s;
+    B200REF_CHECK(pos < M, "k_partition: run slot outside the parameter");
     ok[pos] = sm.skey[s];
     oi[pos] = base + (mm & 0xffffu);
   }
@@ -682,6 +683,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
       for (int j = 0; j < LB; ++j) {
         if ((uint32_t)((it + j) * NT + tid) < n) {
           const uint32_t slot = sm.foff[fr[it + j] & 0xffffu] + (fr[it + j] >> 16);
+          B200REF_CHECK(slot < n && n <= (uint32_t)CAP, "finish_bucket: staging slot outside the tile");
           sm.kd[slot] = key2dbl(kk[j]);
           sm.i2[slot] = ii[j];
         }
@@ -734,6 +736,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
       for (uint32_t t = a; t < s; ++t) eqb += (sm.kd[t] == k);
     const uint32_t i = B0 + a + less;
     const uint32_t pos = i + eqb;
+    B200REF_CHECK(pos >= B0 && pos < B0 + n && (sm.i2[s] & ~TIED_BIT) < M, "finish_bucket: sorted position outside the bucket");
     ok[pos] = dbl2key(k);
     oi[pos] = (eq > 1u) ? (sm.i2[s] | TIED_BIT) : sm.i2[s];
     if (eq > 1u) oc[pos] = 2 * i + eq;  // i + j with j = i + eq
@@ -767,6 +770,7 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
       }
       const uint32_t i = B0 + a + less;
       const uint32_t pos = i + eqb;
+      B200REF_CHECK(pos >= B0 && pos < B0 + n, "finish_bucket (warp path): sorted position outside the bucket");
       ok[pos] = dbl2key(k);
       oi[pos] = (eq > 1u) ? (sm.i2[s] | TIED_BIT) : sm.i2[s];
       if (eq > 1u) oc[pos] = 2 * i + eq;
@@ -982,6 +986,8 @@ __global__ void __launch_bounds__(PART_NT) k_partition_w(const double* __restric
     const uint32_t e = it * PART_NT + tid;
     if (e < n) {
       const uint32_t pos = sm.cnt[bk[it]] + r[it];
+      B200REF_CHECK(pos < M && pos >= b.boff[(size_t)p * b.bstride + bk[it]] && pos < b.boff[(size_t)p * b.bstride + bk[it] + 1],
+                    "k_partition_w: reserved run leaves its bucket");
       ok[pos] = dbl2key(v[it]);
       oi[pos] = base + e;
     }
@@ -1097,6 +1103,7 @@ __global__ void __launch_bounds__(FINB_NT) k_finish_big(uint32_t M, BucketBufs b
     if (b.fallback[p]) continue;
     const uint32_t B0 = b.boff[(size_t)p * b.bstride + cb];
     const uint32_t n = b.boff[(size_t)p * b.bstride + cb + 1] - B0;
+    B200REF_CHECK(q < b.biglist_cap && n <= (uint32_t)CAPBIG && B0 + n <= M, "k_finish_big: list entry out of range");
     __syncthreads();
     finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true, true>(sm, make_fine<NFINE_BIG>(b.fn + p, cb, nsub), B0, n, M, p, b, fo);
   }

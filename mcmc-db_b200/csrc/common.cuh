@@ -7,6 +7,23 @@
 namespace b200ref {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// Checked build (-DB200REF_CHECKED, `python __graft_entry__.py --checked` -> libb200ref_checked.so): every store
+// whose address depends on a scheduling-dependent atomic or on another kernel's output is bounds-checked and a
+// violation traps with a message.  (compute-sanitizer is closed on the GPU pool this was developed on; the checked
+// build run over tools/sanitize_smoke.py and the edge-case tests is the substitute -- profiles/r2/.)
+#ifdef B200REF_CHECKED
+#define B200REF_CHECK(cond, what)                                                                       \
+  do {                                                                                                  \
+    if (!(cond)) {                                                                                      \
+      printf("b200ref CHECK failed: %s (%s:%d, block %d,%d thread %d)\n", what, __FILE__, __LINE__,     \
+             blockIdx.x, blockIdx.y, threadIdx.x);                                                      \
+      __trap();                                                                                         \
+    }                                                                                                   \
+  } while (0)
+#else
+#define B200REF_CHECK(cond, what) ((void)0)
+#endif
 // Bit 31 of a sorted element's original position (C*N < 2^31): the element belongs to a tie run and
 // its code k = i + j is in kcode; an untied element at sorted position t has k = 2t + 1.
 constexpr uint32_t TIED_BIT = 0x80000000u;

@@ -461,6 +461,8 @@ __global__ void __launch_bounds__(RANK_NT, B200REF_FOLD_OCC) k_fold(RankBufs b, 
         fold_score(w, kk, zf);
         const uint32_t r = rr[it] & 31u;
         const size_t slot = pbase + ((size_t)r << o.bin_shift) + bbase[r] + (rr[it] >> 5);
+        B200REF_CHECK(slot < pbase + M && bbase[r] + (rr[it] >> 5) < (1u << o.bin_shift) && pi[it] < M,
+                      "k_fold: record leaves its window segment");
         o.rpos[slot] = pi[it];
         o.rzb[slot] = zb[it];
         o.rzf[slot] = zf;
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(RANK_NT, B200REF_FOLD_OCC) k_fold(RankBufs b, 
       uint32_t kk;
       double zf;
       fold_score(w, kk, zf);
+      B200REF_CHECK(pi[it] < M, "k_fold: original position outside the parameter");
       if (o.zz) {
         __stcs(&o.zz[pbase + pi[it]], make_double2(zb[it], zf));  // streaming store (.cs): -1.5 % against the default policy
       } else {
@@ -506,7 +509,10 @@ __global__ void __launch_bounds__(UNBIN_NT) k_unbin(FoldOut o, const uint8_t* __
   }
 #pragma unroll
   for (int j = 0; j < UNBIN_IPT; ++j)
-    if (s0 + j * UNBIN_NT < M) __stcs(&o.zz[pbase + pos[j]], make_double2(zb[j], zf[j]));
+    if (s0 + j * UNBIN_NT < M) {
+      B200REF_CHECK(pos[j] < M, "k_unbin: record position outside the parameter");
+      __stcs(&o.zz[pbase + pos[j]], make_double2(zb[j], zf[j]));
+    }
 }
 
 }  // namespace b200ref

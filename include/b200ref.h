@@ -116,6 +116,15 @@ int b200ref_diagnostics_ex_f64(const double* x_dev, int64_t P, int64_t C, int64_
                                const double* q_host, int nq, int ess_mode, const b200ref_outputs* out,
                                void* ws_dev, size_t ws_bytes, void* stream);
 
+/* Chain statistics of CALLER-SUPPLIED scores: split R-hat (_split_chains + _rhat, diagnostics.py:76-85, :136-151) and
+ * ESS (_ess / _autocorr, :154-193) of zb_dev [P][C][N] (-> rhat_bulk, ess_bulk, lag_bulk) and zf_dev [P][C][N]
+ * (-> rhat_tail, ess_tail, lag_tail; null: zb again); out->rhat = max of the two.  No ranking happens here: this is
+ * the second half of the fused pass, exposed for inputs whose rank-normalisation was done separately -- the host
+ * layer uses it for RAGGED chains, which the reference rank-normalises over all draws and then truncates to the
+ * shortest chain (diagnostics.py:140,158).  Workspace: b200ref_workspace_bytes(P, C, N). */
+int b200ref_chain_stats_f64(const double* zb_dev, const double* zf_dev, int64_t P, int64_t C, int64_t N, int ess_mode,
+                            const b200ref_outputs* out, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* The same diagnostics for draws in the reference's NUMPY layout: `Draws.to_numpy()` (draws.py:20-29) returns
  * [rows][P] with rows ordered (chain, draw) and the PARAMETER index fastest.  x_rows_dev is that matrix
  * ([C*N][P] fp64, device); the library transposes parameter blocks into its workspace (tiled transposing load)

@@ -336,6 +336,82 @@ __global__ void k_summary(const double* rhat, const double* essb, const double* 
   }
 }
 
+// Opt-in dynamic shared-memory sizes: function attributes are per device; several host threads may arrive at once.
+int ensure_kernel_attributes() {
+  static std::once_flag attr_once[MAX_DEVICES];
+  static cudaError_t attr_err[MAX_DEVICES];
+  const int dev = current_device();
+  std::call_once(attr_once[dev], [dev] {
+    cudaError_t e = cudaSuccess;
+    auto set = [&e](const void* f, size_t bytes) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
+    set((const void*)k_partition, sizeof(PartSmem));
+    set((const void*)k_finish, sizeof(FinSmemSmall));
+    set((const void*)k_finish_big, sizeof(FinSmemBig));
+    set((const void*)k_moments0, sizeof(Mo0Smem));
+    set((const void*)k_ess_rounds, sizeof(RoundsSmem));
+    set((const void*)k_decide0, 3 * (size_t)MAX_CHAINS * sizeof(double));  // 96 KB at the advertised 4096 chains
+    attr_err[dev] = e;
+  });
+  CUDA_TRY(attr_err[dev]);
+  return B200REF_OK;
+}
+
+// Chain statistics of the scores zz[PB][C][N] = {z_bulk, z_folded}: split R-hat, ESS (round 0 for everybody, then the
+// persistent rounds kernel for sticky chains).  `cs.rhat / ess / lag` must be set by the caller; the rest is carved here.
+int launch_chain_stats(const double2* zz, int PB, int64_t C, int64_t N, char* wb, const Layout& L, bool geyer,
+                   cudaStream_t st, ChainState& cs) {
+  // ---- streaming chain statistics: round 0 for everybody, further rounds for sticky chains ----
+  const ChainGeom g = chain_geom(C, N);
+  cs.part = (double*)(wb + L.cpart);
+  cs.partr = (double*)(wb + L.cpartr);
+  cs.cmean = (double*)(wb + L.cmean);
+  cs.csum = (double*)(wb + L.csum);
+  cs.head = (double*)(wb + L.chead);
+  cs.tail = (double*)(wb + L.ctail);
+  cs.varhat = (double*)(wb + L.cvarhat);
+  cs.rhosum = (double*)(wb + L.crhosum);
+  cs.gpend = (double*)(wb + L.cgpend);
+  cs.gprev = (double*)(wb + L.cgprev);
+  cs.geyer = geyer ? 1 : 0;
+  cs.wl[0] = (int*)(wb + L.cwl0);
+  cs.wl[1] = (int*)(wb + L.cwl1);
+  cs.nwl = (int*)(wb + L.cnwl);
+  CUDA_TRY(cudaMemsetAsync(cs.nwl, 0, 2 * sizeof(int), st));
+  if (g.nunits) {
+    // units per CTA: about MO_CTA_TILES sub-tiles of work behind one exposed first copy
+    const uint32_t upc = std::max<uint32_t>(1u, MO_CTA_TILES / g.tpu);
+    const unsigned gx = (unsigned)((C * g.nunits + upc - 1) / upc);
+    LAUNCH(K_CHAIN, st, k_moments0<<<dim3(gx, PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, upc, cs.part));
+  }
+  LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
+  if ((uint32_t)N > 1u + LAGB) {
+    // every later round (32 lags each) in ONE cooperative launch: the grid loops on the device until the
+    // work list is empty -- no list length travels to the host, nothing synchronises between rounds
+    unsigned int* gbar = (unsigned int*)(wb + L.cgbar);
+    CUDA_TRY(cudaMemsetAsync(gbar, 0, sizeof(unsigned int), st));
+    const double2* zzc = zz;
+    ChainGeom gg = g;
+    int pbv = PB;
+    void* args[] = {(void*)&zzc, (void*)&gg, (void*)&pbv, (void*)&cs, (void*)&gbar};
+    const int grid = rounds_grid();
+    if (grid < 1) return fail(B200REF_ERR_CUDA, "k_ess_rounds cannot be made resident on this device");
+    LAUNCH(K_CHAIN, st, CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ess_rounds, dim3((unsigned)grid), dim3(MO_CTA), args,
+                                                            sizeof(RoundsSmem), st)));
+  }
+  return B200REF_OK;
+}
+
+// zz[i] = {zb[i], zf[i]} (zf null: zb twice) -- staging of caller-supplied scores for the chain kernels
+__global__ void k_interleave(const double* __restrict__ zb, const double* __restrict__ zf, int64_t n, double2* __restrict__ zz) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double a = zb[i];
+    zz[i] = make_double2(a, zf ? zf[i] : a);
+  }
+}
+
 struct Mode {
   bool diag;         // run fold + chain kernels
   bool want_ranks;   // scatter average ranks (ranks API)
@@ -370,24 +446,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   int* flag = (int*)(w + L.flag);
   char* wb = w + L.header;
   {
-    // function attributes are per device; several host threads may arrive here at once
-    static std::once_flag attr_once[MAX_DEVICES];
-    static cudaError_t attr_err[MAX_DEVICES];
-    const int dev = current_device();
-    std::call_once(attr_once[dev], [dev] {
-      cudaError_t e = cudaSuccess;
-      auto set = [&e](const void* f, size_t bytes) {
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-      };
-      set((const void*)k_partition, sizeof(PartSmem));
-      set((const void*)k_finish, sizeof(FinSmemSmall));
-      set((const void*)k_finish_big, sizeof(FinSmemBig));
-      set((const void*)k_moments0, sizeof(Mo0Smem));
-      set((const void*)k_ess_rounds, sizeof(RoundsSmem));
-      set((const void*)k_decide0, 3 * (size_t)MAX_CHAINS * sizeof(double));  // 96 KB at the advertised 4096 chains
-      attr_err[dev] = e;
-    });
-    CUDA_TRY(attr_err[dev]);
+    const int rc = ensure_kernel_attributes();
+    if (rc) return rc;
   }
 
   CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -542,44 +602,8 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     cs.ess = (double*)(wb + L.cess);
     cs.lag = (int64_t*)(wb + L.clag);
     if (mode.diag) {
-      // ---- streaming chain statistics: round 0 for everybody, further rounds for sticky chains ----
-      const ChainGeom g = chain_geom(C, N);
-      cs.part = (double*)(wb + L.cpart);
-      cs.partr = (double*)(wb + L.cpartr);
-      cs.cmean = (double*)(wb + L.cmean);
-      cs.csum = (double*)(wb + L.csum);
-      cs.head = (double*)(wb + L.chead);
-      cs.tail = (double*)(wb + L.ctail);
-      cs.varhat = (double*)(wb + L.cvarhat);
-      cs.rhosum = (double*)(wb + L.crhosum);
-      cs.gpend = (double*)(wb + L.cgpend);
-      cs.gprev = (double*)(wb + L.cgprev);
-      cs.geyer = mode.geyer ? 1 : 0;
-      cs.wl[0] = (int*)(wb + L.cwl0);
-      cs.wl[1] = (int*)(wb + L.cwl1);
-      cs.nwl = (int*)(wb + L.cnwl);
-      CUDA_TRY(cudaMemsetAsync(cs.nwl, 0, 2 * sizeof(int), st));
-      if (g.nunits) {
-        // units per CTA: about MO_CTA_TILES sub-tiles of work behind one exposed first copy
-        const uint32_t upc = std::max<uint32_t>(1u, MO_CTA_TILES / g.tpu);
-        const unsigned gx = (unsigned)((C * g.nunits + upc - 1) / upc);
-        LAUNCH(K_CHAIN, st, k_moments0<<<dim3(gx, PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, upc, cs.part));
-      }
-      LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
-      if ((uint32_t)N > 1u + LAGB) {
-        // every later round (32 lags each) in ONE cooperative launch: the grid loops on the device until the
-        // work list is empty -- no list length travels to the host, nothing synchronises between rounds
-        unsigned int* gbar = (unsigned int*)(wb + L.cgbar);
-        CUDA_TRY(cudaMemsetAsync(gbar, 0, sizeof(unsigned int), st));
-        const double2* zzc = zz;
-        ChainGeom gg = g;
-        int pbv = PB;
-        void* args[] = {(void*)&zzc, (void*)&gg, (void*)&pbv, (void*)&cs, (void*)&gbar};
-        const int grid = rounds_grid();
-        if (grid < 1) return fail(B200REF_ERR_CUDA, "k_ess_rounds cannot be made resident on this device");
-        LAUNCH(K_CHAIN, st, CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ess_rounds, dim3((unsigned)grid), dim3(MO_CTA), args,
-                                                                sizeof(RoundsSmem), st)));
-      }
+      const int rc = launch_chain_stats(zz, PB, C, N, wb, L, mode.geyer, st, cs);
+      if (rc) return rc;
     }
     if (out) {
       FinalizeArgs fa;
@@ -694,6 +718,60 @@ int b200ref_diagnostics_ex_f64(const double* x, int64_t P, int64_t C, int64_t N,
   Mode m{true, false, ess_mode == B200REF_ESS_GEYER};
   return run(x, P, C, N, q_host, nq, out, nullptr, nullptr, nullptr, nullptr, m, ws, ws_bytes,
              (cudaStream_t)stream);
+}
+
+int b200ref_chain_stats_f64(const double* zb, const double* zf, int64_t P, int64_t C, int64_t N, int ess_mode,
+                            const b200ref_outputs* out, void* ws, size_t ws_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!out) return fail(B200REF_ERR_ARG, "null outputs");
+  if (!zb || P < 0 || C < 1 || N < 1) return fail(B200REF_ERR_ARG, "bad shape P=%lld C=%lld N=%lld", (long long)P, (long long)C, (long long)N);
+  if (C > MAX_CHAINS) return fail(B200REF_ERR_ARG, "more than %d chains are not supported (C=%lld)", MAX_CHAINS, (long long)C);
+  if (C * N >= (1ll << 31)) return fail(B200REF_ERR_ARG, "C*N = %lld exceeds 2^31-1", (long long)(C * N));
+  if (ess_mode != B200REF_ESS_FIRST_NEGATIVE && ess_mode != B200REF_ESS_GEYER)
+    return fail(B200REF_ERR_ARG, "unknown ess_mode %d", ess_mode);
+  if (P == 0) return B200REF_OK;
+  if (!ws) return fail(B200REF_ERR_WORKSPACE, "null workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = C * N;
+  const int64_t PBmax = fit_batch(P, M, true, ws_bytes, BATCH_CAP, C, N);
+  if (PBmax < 1) return fail(B200REF_ERR_WORKSPACE, "workspace of %zu bytes cannot hold one parameter", ws_bytes);
+  Layout L;
+  L.compute(PBmax, M, true, C, N);
+  char* wb = (char*)ws + L.header;
+  {
+    int rc = ensure_kernel_attributes();
+    if (rc) return rc;
+  }
+  for (int64_t p0 = 0; p0 < P; p0 += PBmax) {
+    const int PB = (int)std::min<int64_t>(PBmax, P - p0);
+    double2* zz = (double2*)(wb + L.zz);
+    const int64_t n = (int64_t)PB * M;
+    LAUNCH(K_INGEST, st, k_interleave<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
+                             zb + (size_t)p0 * M, zf ? zf + (size_t)p0 * M : nullptr, n, zz));
+    ChainState cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.rhat = (double*)(wb + L.crhat);
+    cs.ess = (double*)(wb + L.cess);
+    cs.lag = (int64_t*)(wb + L.clag);
+    int rc = launch_chain_stats(zz, PB, C, N, wb, L, ess_mode == B200REF_ESS_GEYER, st, cs);
+    if (rc) return rc;
+    FinalizeArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.crhat = cs.rhat;
+    fa.cess = cs.ess;
+    fa.clag = (const long long*)cs.lag;
+    fa.rhat = out->rhat ? out->rhat + p0 : nullptr;
+    fa.rhat_bulk = out->rhat_bulk ? out->rhat_bulk + p0 : nullptr;
+    fa.rhat_tail = out->rhat_tail ? out->rhat_tail + p0 : nullptr;
+    fa.ess_bulk = out->ess_bulk ? out->ess_bulk + p0 : nullptr;
+    fa.ess_tail = out->ess_tail ? out->ess_tail + p0 : nullptr;
+    fa.lag_bulk = out->lag_bulk ? out->lag_bulk + p0 : nullptr;
+    fa.lag_tail = out->lag_tail ? out->lag_tail + p0 : nullptr;
+    LAUNCH(K_FINALIZE, st, k_finalize<<<(PB + 127) / 128, 128, 0, st>>>(fa, (uint32_t)M, PB));
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return B200REF_OK;
 }
 
 int b200ref_transpose_rows_f64(const double* in, int64_t M, int64_t P, int64_t p0, int64_t PB, double* out, void* stream) {

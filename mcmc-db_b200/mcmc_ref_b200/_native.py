@@ -29,6 +29,7 @@ EXPORTS = (
     "b200ref_glm_workspace_bytes", "b200ref_glm_logistic_lp_f64", "b200ref_glm_lp_f64", "b200ref_glm_lp_ex_f64",
     "b200ref_row_order_i64", "b200ref_gather_rows_f64",
     "b200ref_rows_workspace_bytes", "b200ref_diagnostics_layout_f64", "b200ref_transpose_rows_f64",
+    "b200ref_chain_stats_f64",
 )
 GLM_REUSE_DESIGN = 1
 LAYOUTS = {"pcn": 0, "rows": 1}
@@ -99,6 +100,7 @@ def load() -> C.CDLL:
     lib.b200ref_rows_workspace_bytes.argtypes = [i64, i64, i64]
     lib.b200ref_diagnostics_layout_f64.argtypes = [vp, C.c_int, i64, i64, i64, C.POINTER(dbl), C.c_int, C.c_int,
                                                    C.POINTER(Outputs), vp, sz, vp]
+    lib.b200ref_chain_stats_f64.argtypes = [vp, vp, i64, i64, i64, C.c_int, C.POINTER(Outputs), vp, sz, vp]
     lib.b200ref_transpose_rows_f64.argtypes = [vp, i64, i64, i64, i64, vp, vp]
     for name in EXPORTS:  # every symbol include/b200ref.h declares must be exported
         getattr(lib, name)

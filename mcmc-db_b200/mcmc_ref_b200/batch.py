@@ -37,6 +37,11 @@ def to_device(x) -> torch.Tensor:
     return t.contiguous()
 
 
+def to_index(rows) -> torch.Tensor:
+    """int64 CUDA index tensor from a host array."""
+    return torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).to(_device())
+
+
 def _stream_ptr() -> int:
     return int(torch.cuda.current_stream().cuda_stream)
 
@@ -116,6 +121,27 @@ def _alloc_outputs(p: int, nq: int, diag: bool, dev) -> tuple[dict[str, torch.Te
     for name, _ in _native.Outputs._fields_:
         setattr(o, name, t[name].data_ptr() if name in t else None)
     return t, o
+
+
+def chain_stats_batch(z_bulk, z_folded=None, workspace: Workspace | None = None,
+                      ess_truncation: str = "first_negative") -> dict[str, torch.Tensor]:
+    """Split R-hat and ESS of already rank-normalised scores ``z_bulk`` / ``z_folded`` [P, C, N] (the second half of the
+    fused pass: ``_split_chains`` + ``_rhat`` + ``_ess``, diagnostics.py:76-85, :136-193)."""
+    if ess_truncation not in _native.ESS_MODES:
+        raise ValueError(f"ess_truncation must be one of {sorted(_native.ESS_MODES)}; got {ess_truncation!r}")
+    lib = _native.load()
+    zb = to_device(z_bulk)
+    zf = to_device(z_folded) if z_folded is not None else None
+    p, c, n = zb.shape
+    if zf is not None and zf.shape != zb.shape:
+        raise ValueError("z_bulk and z_folded must have the same shape")
+    t, o = _alloc_outputs(p, 0, True, zb.device)
+    if p == 0:
+        return t
+    ws = (workspace or _WS).for_shape(p, c, n)
+    _native.check(lib.b200ref_chain_stats_f64(zb.data_ptr(), _ptr(zf), p, c, n, _native.ESS_MODES[ess_truncation],
+                                              C.byref(o), ws.data_ptr(), ws.numel(), _stream_ptr()))
+    return {k: t[k] for k in ("rhat", "rhat_bulk", "rhat_tail", "ess_bulk", "ess_tail", "lag_bulk", "lag_tail")}
 
 
 def diagnostics_rows(x_rows, n_chains: int, quantiles=_DEFAULT_Q, workspace: Workspace | None = None,

@@ -298,3 +298,28 @@ def test_heavy_ties_stay_on_the_fast_path(B):
         ms[name] = best * 1e3
     print(f"heavy ties: continuous {ms['cont']:.2f} ms, 50 % zeros {ms['half_zero']:.2f} ms")
     assert ms["half_zero"] < 3.0 * ms["cont"], ms
+
+
+def test_ragged_chains_follow_the_reference(B):
+    """Chains of different lengths (fixture from the unmodified reference, `make_ragged_golden.py`): pooled ranks over
+    all draws, each chain split at its own midpoint, every (split) chain truncated to the shortest one."""
+    from conftest import dec
+    from mcmc_ref_b200 import diagnostics as D
+
+    cases = json.loads((GOLDEN / "ragged_cases.json").read_text())
+    assert len(cases) >= 9
+    for case in cases:
+        chains = case["chains"]
+        got = D.diagnostics(chains)
+        for k in ("rhat", "ess_bulk", "ess_tail"):
+            assert close(got[k], dec(case[k]), TOL), (case["name"], k, got[k], case[k])
+        assert close(D.split_rhat(chains), dec(case["rhat"]), TOL), case["name"]
+        assert close(D.ess_bulk(chains), dec(case["ess_bulk"]), TOL) and close(D.ess_tail(chains), dec(case["ess_tail"]), TOL)
+    # the chain-statistics entry point on its own: scores in, R-hat / ESS out == the fused pass on equal chains
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((3, 4, 500)) + rng.standard_normal((3, 4, 1)) * 0.1
+    r = B.ranks_batch(x)
+    st = B.chain_stats_batch(r["z"], r["z_folded"])
+    d = B.diagnostics_batch(x)
+    for k in ("rhat", "rhat_bulk", "rhat_tail", "ess_bulk", "ess_tail", "lag_bulk", "lag_tail"):
+        assert np.array_equal(st[k].cpu().numpy(), d[k].cpu().numpy(), equal_nan=True), k

@@ -223,7 +223,7 @@ def diag_measure(args, wname: str, rank: int, world: int, local: int, full: bool
         "config": make_config(w, world), "compare_passed": passed,
         "clocks": clocks, "gpu_launches": int(nl.item()), "pass_roofline": pass_roofline, "roofline": roofline,
     }
-    if not full:
+    if not full or args.no_e2e:
         del cand, ref, ws
         torch.cuda.empty_cache()
         return line
@@ -531,6 +531,7 @@ def main() -> None:
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"],
                     help="--impl reference: the unmodified reference from oracle/_ref, or the numpy port")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel-tuning runs: device-timed value and roofline blocks only")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -1157,7 +1157,20 @@ struct GlmLayout {
     Dpad = (int)((D + GLM_BK - 1) / GLM_BK * GLM_BK);
     n_row_tiles = (int)((N + GLM_BN - 1) / GLM_BN);
     n_draw_tiles = (int)((S + GLM_BM - 1) / GLM_BM);
-    nsplit = std::max(1, std::min(std::min(8, n_row_tiles), (4 * 148 + n_draw_tiles - 1) / n_draw_tiles));
+    // row-tile slices per draw tile: the persistent grid (one CTA per SM) runs ceil(items / SMs) waves of
+    // ceil(n_row_tiles / nsplit) tiles each -- take the split that minimises waves x tiles (ties: fewer slices).
+    // With few draw tiles (a draw-block shard of a multi-GPU run) this fills the last wave: 64 draw tiles x 37
+    // slices = 16 full waves on 148 SMs, where 8 slices left 0.54 of a wave idle.
+    {
+      const int nsm = 148;
+      long best = -1;
+      nsplit = 1;
+      for (int k = 1; k <= std::min(64, n_row_tiles); ++k) {
+        const long waves = ((long)n_draw_tiles * k + nsm - 1) / nsm;
+        const long cost = waves * ((n_row_tiles + k - 1) / k) * 64 + k;  // + k: one partial-sum pass per slice
+        if (best < 0 || cost < best) { best = cost; nsplit = k; }
+      }
+    }
     size_t o = 0;
     bh = o; o += up((size_t)S * Dpad * 2);
     bl = o; o += up((size_t)S * Dpad * 2);

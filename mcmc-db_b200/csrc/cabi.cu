@@ -1158,18 +1158,17 @@ struct GlmLayout {
     n_row_tiles = (int)((N + GLM_BN - 1) / GLM_BN);
     n_draw_tiles = (int)((S + GLM_BM - 1) / GLM_BM);
     // row-tile slices per draw tile: the persistent grid (one CTA per SM) runs ceil(items / SMs) waves of
-    // ceil(n_row_tiles / nsplit) tiles each -- take the split that minimises waves x tiles (ties: fewer slices).
-    // With few draw tiles (a draw-block shard of a multi-GPU run) this fills the last wave: 64 draw tiles x 37
-    // slices = 16 full waves on 148 SMs, where 8 slices left 0.54 of a wave idle.
+    // ceil(n_row_tiles / nsplit) tiles each.  Few slices keep the CTAs of a wave on the same rows of X (they share
+    // them through L2: 17 slices instead of 2 cost 5 % at config 3), so the SMALLEST split within 4 % of the best
+    // waves x tiles is taken.  With few draw tiles (a draw-block shard of a multi-GPU run) that fills the last wave:
+    // 64 draw tiles x 9 slices = 3.9 waves of 44 tiles, where 8 slices ran 4 waves of 49.
     {
-      const int nsm = 148;
-      long best = -1;
+      const int nsm = 148, kmax = std::min(64, n_row_tiles);
+      auto cost = [&](int k) { return (((long)n_draw_tiles * k + nsm - 1) / nsm) * ((n_row_tiles + k - 1) / k); };
+      long best = cost(1);
+      for (int k = 2; k <= kmax; ++k) best = std::min(best, cost(k));
       nsplit = 1;
-      for (int k = 1; k <= std::min(64, n_row_tiles); ++k) {
-        const long waves = ((long)n_draw_tiles * k + nsm - 1) / nsm;
-        const long cost = waves * ((n_row_tiles + k - 1) / k) * 64 + k;  // + k: one partial-sum pass per slice
-        if (best < 0 || cost < best) { best = cost; nsplit = k; }
-      }
+      while (nsplit < kmax && cost(nsplit) * 100 > best * 104) ++nsplit;
     }
     size_t o = 0;
     bh = o; o += up((size_t)S * Dpad * 2);

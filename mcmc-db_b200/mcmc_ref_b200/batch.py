@@ -145,7 +145,7 @@ def chain_stats_batch(z_bulk, z_folded=None, workspace: Workspace | None = None,
 
 
 def diagnostics_rows(x_rows, n_chains: int, quantiles=_DEFAULT_Q, workspace: Workspace | None = None,
-                     ess_truncation: str = "first_negative") -> dict[str, torch.Tensor]:
+                     ess_truncation: str = "first_negative", ws_cap_bytes: int | None = None) -> dict[str, torch.Tensor]:
     """The same diagnostics for draws in the reference's numpy layout: ``x_rows[C * N, P]``, rows ordered
     (chain, draw), PARAMETER fastest -- what ``Draws.to_numpy()`` / ``reference.draws(return_="numpy")`` return
     (draws.py:20-29).  The library transposes parameter blocks on the device (tiled transposing load) and runs
@@ -165,8 +165,13 @@ def diagnostics_rows(x_rows, n_chains: int, quantiles=_DEFAULT_Q, workspace: Wor
     t, o = _alloc_outputs(p, len(qs), True, xt.device)
     if p == 0:
         return t
-    ws = (workspace or _WS).ensure(int(lib.b200ref_rows_workspace_bytes(p, c, n)))
+    want = int(lib.b200ref_rows_workspace_bytes(p, c, n))
+    if ws_cap_bytes is not None:  # a smaller workspace makes the library walk the parameters in several blocks
+        want = max(min(want, int(ws_cap_bytes)), int(lib.b200ref_rows_workspace_bytes(1, c, n)))
+    ws = (workspace or _WS).ensure(want)
+    ws_view = ws[:want]
     qarr = (C.c_double * max(len(qs), 1))(*qs)
+    ws = ws_view
     _native.check(lib.b200ref_diagnostics_layout_f64(xt.data_ptr(), _native.LAYOUTS["rows"], p, c, n, qarr, len(qs),
                                                      _native.ESS_MODES[ess_truncation], C.byref(o),
                                                      ws.data_ptr(), ws.numel(), _stream_ptr()))

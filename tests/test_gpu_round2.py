@@ -251,8 +251,35 @@ def test_numpy_layout_rows_param_fastest(B):
         got = B.diagnostics_rows(rows, n_chains=c)
         for k, v in want.items():
             assert np.array_equal(v.cpu().numpy(), got[k].cpu().numpy(), equal_nan=True), (p, c, n, k)
+    # a workspace that holds only a few parameters: several transposed blocks, same bits
+    from mcmc_ref_b200 import _native
+
+    lib = _native.load()
+    x = rng.standard_normal((29, 4, 700))
+    rows = np.ascontiguousarray(x.reshape(29, -1).T)
+    want = B.diagnostics_batch(x)
+    got = B.diagnostics_rows(rows, n_chains=4, workspace=B.Workspace(), ws_cap_bytes=int(lib.b200ref_rows_workspace_bytes(5, 4, 700)))
+    for k, v in want.items():
+        assert np.array_equal(v.cpu().numpy(), got[k].cpu().numpy(), equal_nan=True), ("blocks", k)
     with pytest.raises(ValueError, match="equal chains"):
         B.diagnostics_rows(np.zeros((10, 3)), n_chains=4)
+
+
+def test_very_sticky_chains_reach_the_two_tile_rounds(B):
+    """Autocorrelation that stays positive past lag 1041: the persistent rounds kernel switches from its single-tile
+    to its two-tile variant in mid-flight (shared mbarrier phase, same work list).  Lags compared for equality."""
+    from scipy.signal import lfilter
+
+    rng = np.random.default_rng(123)
+    c, n, phi = 4, 60_000, 0.9995
+    x = lfilter([math.sqrt(1 - phi * phi)], [1.0, -phi], rng.standard_normal((c, n)), axis=1)
+    d = B.diagnostics_batch(np.stack([x, rng.standard_normal((c, n))]))
+    want = O.diagnostics_param(x)
+    assert want["lag_bulk"] > 1100, want["lag_bulk"]  # really past the single-tile rounds
+    for k in ("rhat", "ess_bulk", "ess_tail"):
+        assert close(float(d[k][0].item()), want[k], TOL), (k, float(d[k][0].item()), want[k])
+    assert int(d["lag_bulk"][0].item()) == want["lag_bulk"] and int(d["lag_tail"][0].item()) == want["lag_tail"]
+    assert float(d["ess_bulk"][1].item()) > 0.5 * c * n  # the well-mixed parameter of the same batch is untouched
 
 
 def test_heavy_ties_stay_on_the_fast_path(B):

@@ -523,7 +523,7 @@ def main() -> None:
     ap.add_argument("--glm-d", type=int, default=256)
     ap.add_argument("--glm-s", type=int, default=65_536)
     ap.add_argument("--glm-cpu-draws", type=int, default=512)
-    ap.add_argument("--ws-gb", type=float, default=16.0, help="cap of the device workspace")
+    ap.add_argument("--ws-gb", type=float, default=32.0, help="cap of the device workspace")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-draws-per-core", type=float, default=1.0e7,
                     help="cpu_baseline leg: draws each host core gets (sample = that many parameters)")

@@ -68,6 +68,10 @@ struct BucketFn {
   int nb1;
   int sub;            // sub-buckets per coarse bucket (1: the coarse buckets are the buckets)
   double fsub[NB1_MAX];  // sub / (upper - lower) of coarse bucket c, 0 if degenerate
+  // single-pass partition (k_part1): coarse bucket c owns records [soff[c], soff[c + 1]) of the parameter's slab
+  // region; slab_ok = 0: the capacities do not fit the region (the parameter goes to the LSD path)
+  uint32_t soff[NB1_MAX + 1];
+  int slab_ok;
 };
 
 __host__ __device__ inline int choose_nb1(int64_t M) {
@@ -136,8 +140,11 @@ struct BucketBufs {
   int* nfb;            // number of fallback parameters in this batch
   int* plist;          // [PB] their indices (compact, arbitrary order)
   int* flag;           // bit0 non-finite input
-  uint64_t* pkey;      // [PB][M] partitioned keys
-  uint32_t* pidx;      // [PB][M] partitioned positions
+  uint64_t* pkey;      // [PB][pstride] partitioned keys
+  uint32_t* pidx;      // [PB][pstride] partitioned positions
+  size_t pstride;      // records per parameter in pkey / pidx: M (dense, two-pass partition) or the slab region
+  int slab;            // 1: single-pass partition -- bucket c's records start at fn->soff[c] (narrow path only)
+  uint32_t slab_cap;   // records of one parameter's slab region
   uint64_t* skey;      // [PB][M] sorted keys
   uint32_t* sidx;      // [PB][M] sorted positions
   uint32_t* bmeta;     // [PB][M] narrow path, between k_bhist and k_partition: bucket << 16 | arrival rank of the
@@ -242,6 +249,60 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     int a = 0, e = nb1 - 1;
     while (a < e) { const int mid = (a + e) >> 1; if (scell[mid] < c) a = mid + 1; else e = mid; }
     fn->lut[c] = (uint16_t)a;
+  }
+  if (b.slab) {
+    // Single-pass partition: capacity of every coarse bucket's slab.  A bucket holds M / nb1 draws on average with
+    // a relative spread of 1 / sqrt(OVERSAMPLE) (its bounds are sample quantiles): three times the mean is beyond
+    // 8 sigma, and also covers a repeated value too rare to show up as duplicate splitters (< 2 / nb1 of the
+    // draws).  A pure bucket (copies of one value) is sized from the number of copies in the sample, + 6 sigma.
+    __shared__ uint32_t capv[NB1_MAX];
+    __syncthreads();  // the splitters in fn->sp are final
+    for (int j = threadIdx.x; j < NB1_MAX; j += 512) {
+      uint32_t c = 0;
+      if (j < nb1) {
+        c = min(M, 3u * ((M + (uint32_t)nb1 - 1u) / (uint32_t)nb1) + 64u);
+        if (coarse_is_pure(fn->sp, nb1, j)) {
+          const uint64_t kv = dbl2key(fn->sp[j - 1]);
+          uint32_t l0 = 0, h0 = S;  // first sample >= v
+          while (l0 < h0) { const uint32_t mid = (l0 + h0) >> 1; if (s[mid] < kv) l0 = mid + 1; else h0 = mid; }
+          uint32_t l1 = l0, h1 = S;  // first sample > v
+          while (l1 < h1) { const uint32_t mid = (l1 + h1) >> 1; if (s[mid] <= kv) l1 = mid + 1; else h1 = mid; }
+          const double cs_ = (double)(l1 - l0);
+          const double est = ceil((cs_ + 6.0 * sqrt(cs_) + 16.0) * ((double)M / (double)S));
+          const uint32_t ce = (est < (double)M) ? (uint32_t)est : M;
+          c = max(c, ce);
+        }
+      }
+      capv[j] = c;
+    }
+    __syncthreads();
+    {  // exclusive prefix of the capacities (each <= M < 2^31, 256 of them: 64-bit sums)
+      __shared__ unsigned long long cw[NB1_MAX / 32];
+      const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+      unsigned long long incl = 0, own = 0;
+      if (t < NB1_MAX) {
+        own = capv[t];
+        incl = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long nn = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += nn;
+        }
+        if (lane == 31) cw[w] = incl;
+      }
+      __syncthreads();
+      if (t < NB1_MAX) {
+        unsigned long long pre = 0;
+        for (int k = 0; k < w; ++k) pre += cw[k];
+        const unsigned long long ex = pre + incl - own;
+        fn->soff[t] = (uint32_t)min(ex, 0xffffffffull);
+        if (t == NB1_MAX - 1) {
+          const unsigned long long tot = ex + own;
+          fn->soff[NB1_MAX] = (uint32_t)min(tot, 0xffffffffull);
+          fn->slab_ok = (tot <= (unsigned long long)b.slab_cap) ? 1 : 0;
+        }
+      }
+    }
   }
 }
 
@@ -478,8 +539,8 @@ __global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const d
     }
   }
   __syncthreads();
-  uint64_t* ok = b.pkey + (size_t)p * M;
-  uint32_t* oi = b.pidx + (size_t)p * M;
+  uint64_t* ok = b.pkey + (size_t)p * b.pstride;
+  uint32_t* oi = b.pidx + (size_t)p * b.pstride;
 #pragma unroll 4
   for (uint32_t s = tid; s < n; s += PART_NT) {
     const uint32_t mm = sm.smeta[s];
@@ -487,6 +548,211 @@ __global__ void __launch_bounds__(PART_NT, B200REF_PART_OCC) k_partition(const d
     B200REF_CHECK(pos < M, "k_partition: run slot outside the parameter");
     ok[pos] = sm.skey[s];
     oi[pos] = base + (mm & 0xffffu);
+  }
+}
+
+// ---------------------------------------------------------------- k_part1 / k_bscan1: single-pass partition
+// The draws are read ONCE: bucket function, chunk histogram (the returning shared-memory atomic is the draw's place
+// in its chunk's run), shifted power sums and the finiteness check as in k_bhist, then -- instead of a second pass
+// over the draws after a global scan -- every (chunk, bucket) run is reserved in the bucket's slack-padded slab
+// with one global atomic (capacities fn->soff, sized by k_sample) and the chunk leaves through the same
+// bucket-ordered staging tile as in k_partition.  The order inside a bucket then depends on scheduling, the
+// RESULTS do not: k_finish ranks by value and draws with equal values receive equal scores.  A run that does
+// not fit its slab marks the parameter for the LSD path (fallback) and is not written.
+struct Part1Smem {
+  uint64_t skey[CHUNK_P];   // the chunk's keys in bucket order
+  uint32_t smeta[CHUNK_P];  // bucket << 16 | index inside the chunk
+  double sp[NB1_MAX];
+  uint32_t cnt[NB1_MAX];    // the chunk's bucket counts
+  uint32_t coff[NB1_MAX];   // start of each bucket inside the chunk
+  uint32_t delta[NB1_MAX];  // (start of this chunk's run in the parameter's slab region) - coff; PART1_DEAD: not written
+  uint32_t wtot[NB1_MAX / 32];
+  double red[2 * 32];
+  uint16_t lut[NCELL + 2];
+};
+constexpr uint32_t PART1_DEAD = 0x80000000u;  // + any slot of the chunk stays above every slab region (pstride < 2^31)
+
+#ifndef B200REF_PART1_NT
+#define B200REF_PART1_NT 256
+#endif
+#ifndef B200REF_PART1_OCC
+#define B200REF_PART1_OCC 4
+#endif
+#ifndef B200REF_PART1_REREAD
+#define B200REF_PART1_REREAD 1  // 1: the draws are read again (L2 hits) for the staging step instead of held in registers
+#endif
+constexpr int P1_NT = B200REF_PART1_NT;     // threads per chunk CTA (the first NB1_MAX of them own one bucket each)
+constexpr int P1_IPT = CHUNK_P / P1_NT;
+static_assert(P1_NT >= NB1_MAX && CHUNK_P % P1_NT == 0, "k_part1: one thread per bucket, whole draws per thread");
+
+__global__ void __launch_bounds__(P1_NT, B200REF_PART1_OCC) k_part1(const double* __restrict__ x, uint32_t M, uint32_t nchunks,
+                                                                    BucketBufs b) {
+  extern __shared__ __align__(16) unsigned char part_smem_raw[];
+  Part1Smem& sm = *reinterpret_cast<Part1Smem*>(part_smem_raw);
+  const int p = blockIdx.y;
+  const uint32_t chunk = blockIdx.x;
+  const BucketFn* fn = b.fn + p;
+  const double* xp = x + (size_t)p * M;
+  const int tid = threadIdx.x;
+  const uint32_t base = chunk * CHUNK_P;
+  const uint32_t n = min((uint32_t)CHUNK_P, M - base);
+  // the chunk's draws are in flight while the bucket function's tables arrive
+  double v[P1_IPT];
+#pragma unroll
+  for (int it = 0; it < P1_IPT; ++it) v[it] = xp[base + min((uint32_t)(it * P1_NT + tid), n - 1)];
+  for (int i = tid; i < NB1_MAX; i += P1_NT) { sm.sp[i] = fn->sp[i]; sm.cnt[i] = 0; }
+  for (int i = tid; i < NCELL + 2; i += P1_NT) sm.lut[i] = fn->lut[i];
+  const double lo = fn->lo, cs = fn->cs, c0 = fn->c0;
+  const int slab_ok = fn->slab_ok;
+  __syncthreads();
+  uint32_t cr[P1_IPT];  // bucket << 16 | arrival rank in the chunk's share of the bucket
+  double s1 = 0.0, s2 = 0.0;
+  bool bad = false;
+#pragma unroll
+  for (int it = 0; it < P1_IPT; ++it) {
+    const uint32_t e = it * P1_NT + tid;
+    if (e < n) {
+      const uint32_t c = (uint32_t)coarse_of(v[it], lo, cs, sm.sp, sm.lut);
+      cr[it] = (c << 16) | atomicAdd(&sm.cnt[c], 1u);
+      bad |= !is_finite_bits(v[it]);
+      const double d = v[it] - c0;
+      s1 += d;
+      s2 = fma(d, d, s2);
+    }
+  }
+  // deterministic block sums (fixed tree), as in k_bhist
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int lane = tid & 31, w = tid >> 5;
+  if (lane == 0) { sm.red[w] = s1; sm.red[32 + w] = s2; }
+  const int anybad = __syncthreads_or(bad);
+  if (tid == 0) {
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < P1_NT / 32; ++k) { a += sm.red[k]; c += sm.red[32 + k]; }
+    b.spart[((size_t)p * nchunks + chunk) * 2 + 0] = a;
+    b.spart[((size_t)p * nchunks + chunk) * 2 + 1] = c;
+    if (anybad) atomicOr(b.flag, 1);
+  }
+  // exclusive scan of the chunk's counts -> coff; one global atomic per non-empty bucket reserves its run (its
+  // round trip is hidden under the staging step: the run's start is only needed when the tile leaves)
+  const bool owner = tid < NB1_MAX;  // thread t < 256 owns bucket t
+  const uint32_t cnt_t = owner ? sm.cnt[tid] : 0u;
+  const bool live = cnt_t != 0 && slab_ok;
+  uint32_t g = 0, s0 = 0, cap = 0;
+  if (live) {
+    s0 = fn->soff[tid];
+    cap = fn->soff[tid + 1] - s0;
+    g = atomicAdd(&b.cur[(size_t)p * NB1_MAX + tid], cnt_t);
+  }
+  uint32_t co;
+  {
+    uint32_t incl = cnt_t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t nn = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += nn;
+    }
+    if (lane == 31 && owner) sm.wtot[w] = incl;
+    __syncthreads();
+    uint32_t pre = (lane < w && lane < NB1_MAX / 32) ? sm.wtot[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
+    co = pre + incl - cnt_t;
+    if (owner) sm.coff[tid] = co;
+  }
+#if B200REF_PART1_REREAD
+#pragma unroll
+  for (int it = 0; it < P1_IPT; ++it) v[it] = xp[base + min((uint32_t)(it * P1_NT + tid), n - 1)];
+#endif
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < P1_IPT; ++it) {
+    const uint32_t e = it * P1_NT + tid;
+    if (e < n) {
+      const uint32_t slot = sm.coff[cr[it] >> 16] + (cr[it] & 0xffffu);
+      sm.skey[slot] = dbl2key(v[it]);
+      sm.smeta[slot] = (cr[it] & 0xffff0000u) | e;
+    }
+  }
+  {
+    uint32_t dl = PART1_DEAD;
+    if (live) {
+      if (g + cnt_t <= cap) dl = s0 + g - co;   // (mod 2^32; dl + slot is the record's place in the region)
+      else b.fallback[p] = 1;                   // slab overflow: k_bscan1 lists the parameter for the LSD path
+    }
+    if (owner) sm.delta[tid] = dl;
+  }
+  __syncthreads();
+  uint64_t* ok = b.pkey + (size_t)p * b.pstride;
+  uint32_t* oi = b.pidx + (size_t)p * b.pstride;
+  const uint32_t lim = (uint32_t)b.pstride;
+#pragma unroll 4
+  for (uint32_t s = tid; s < n; s += P1_NT) {
+    const uint32_t mm = sm.smeta[s];
+    const uint32_t pos = sm.delta[mm >> 16] + s;
+    if (pos < lim) {  // dead runs (slab overflow, no slab) land above every region
+      B200REF_CHECK(pos >= fn->soff[mm >> 16] && pos < fn->soff[(mm >> 16) + 1], "k_part1: record outside its bucket's slab");
+      ok[pos] = sm.skey[s];
+      oi[pos] = base + (mm & 0xffffu);
+    }
+  }
+}
+
+// Bucket totals (the slab cursors) -> sorted offsets, classification of the buckets, mean / std: k_bscan's job
+// without the per-chunk offsets.
+__global__ void __launch_bounds__(NB1_MAX) k_bscan1(uint32_t M, uint32_t nchunks, BucketBufs b) {
+  __shared__ uint32_t wtot[NB1_MAX / 32];
+  __shared__ int over;
+  const int p = blockIdx.x;
+  const int t = threadIdx.x;
+  if (t == 0) over = 0;
+  __syncthreads();
+  const uint32_t run = b.cur[(size_t)p * NB1_MAX + t];
+  const bool pure = coarse_is_pure(b.fn[p].sp, b.fn[p].nb1, t);
+  if (pure) {
+    // any size (inside its slab): k_finish streams it
+  } else if (run > (uint32_t)CAPBIG) {
+    over = 1;
+  } else if (run > (uint32_t)CAP1) {
+    const int slot = atomicAdd(b.nbigb, 1);
+    if (slot < b.biglist_cap) { b.biglist[2 * slot] = p; b.biglist[2 * slot + 1] = t; }
+    else over = 1;  // list full: sort the whole parameter by the LSD path instead
+  }
+  const int lane = t & 31, w = t >> 5;
+  uint32_t incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint32_t pre = (lane < w) ? wtot[lane] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
+  const uint32_t excl = pre + incl - run;
+  b.boff[(size_t)p * b.bstride + t] = excl;
+  if (t == NB1_MAX - 1) {
+    b.boff[(size_t)p * b.bstride + NB1_MAX] = excl + run;
+    if (excl + run != M) over = 1;  // a run was dropped (slab overflow / no slab): nothing of this partition is used
+  }
+  if (t == 0) {
+    // mean = c0 + S1/M ; var = (S2 - S1^2/M)/M  (sums about the sample median: no cancellation)
+    double s1 = 0.0, s2 = 0.0;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+      s1 += b.spart[((size_t)p * nchunks + c) * 2 + 0];
+      s2 += b.spart[((size_t)p * nchunks + c) * 2 + 1];
+    }
+    const double dm = (double)M;
+    const double m1 = s1 / dm;
+    b.mean[p] = b.fn[p].c0 + m1;
+    const double var = (s2 - s1 * m1) / dm;
+    b.sd[p] = sqrt(var > 0.0 ? var : 0.0);
+  }
+  __syncthreads();
+  if (t == 0 && (over || b.fallback[p] || !b.fn[p].slab_ok)) {
+    b.fallback[p] = 1;
+    b.plist[atomicAdd(b.nfb, 1)] = p;
   }
 }
 
@@ -635,15 +901,16 @@ __device__ __forceinline__ int fine_bucket(const FineFn& ff, double x) {
 // TWO_PASS = false: the bucket is read once into registers (n <= NT * IPT);
 // TWO_PASS = true : any n <= CAP, the bucket is read twice and slots come from cursors.
 template <int NT, int NF, int CAP, int IPT, bool TWO_PASS, bool EDGE>
-__device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn ff, uint32_t B0, uint32_t n,
+__device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn ff, uint32_t B0, uint32_t S0, uint32_t n,
                                               uint32_t M, int p, const BucketBufs& b, const FinishOut& fo) {
   const int tid = threadIdx.x;
   auto fine = [&](double x) -> int { return fine_bucket<NF, EDGE>(ff, x); };
   for (int i = tid; i < NF; i += NT) sm.fh[i] = 0;
   if (tid == 0) sm.nbig = 0;
   __syncthreads();
-  const uint64_t* pk = b.pkey + (size_t)p * M + B0;
-  const uint32_t* pi = b.pidx + (size_t)p * M + B0;
+  // B0: the bucket's offset in the sorted order; S0: where its partitioned records start (= B0 unless slabs)
+  const uint64_t* pk = b.pkey + (size_t)p * b.pstride + S0;
+  const uint32_t* pi = b.pidx + (size_t)p * b.pstride + S0;
   if constexpr (!TWO_PASS) {
     // Only the packed word (fine bucket | arrival rank in it << 16, both below 2^16) of every draw stays in
     // registers across the scan; key and position are read again afterwards (L1 / L2 hits).  Holding them too
@@ -979,8 +1246,8 @@ __global__ void __launch_bounds__(PART_NT) k_partition_w(const double* __restric
       if (c[j]) sm.cnt[i0 + j * PART_NT] = r[j];
   }
   __syncthreads();
-  uint64_t* ok = b.pkey + (size_t)p * M;
-  uint32_t* oi = b.pidx + (size_t)p * M;
+  uint64_t* ok = b.pkey + (size_t)p * b.pstride;
+  uint32_t* oi = b.pidx + (size_t)p * b.pstride;
 #pragma unroll
   for (int it = 0; it < PART_IPT; ++it) {
     const uint32_t e = it * PART_NT + tid;
@@ -1025,31 +1292,36 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
   extern __shared__ __align__(16) unsigned char fin_smem_raw[];
   FinSmemSmall& sm = *reinterpret_cast<FinSmemSmall*>(fin_smem_raw);
   __shared__ uint32_t sbo[FIN_BPC + 2];
+  __shared__ uint32_t sso[FIN_BPC + 2];  // where each bucket's partitioned records start (slabs: fn->soff)
   const int p = blockIdx.y, tid = threadIdx.x;
   const int cb0 = blockIdx.x * FIN_BPC;
   if (cb0 >= nbt) return;
   const BucketFn* fn = b.fn + p;
   const uint8_t fb = b.fallback[p];
-  if (tid <= FIN_BPC) sbo[tid] = b.boff[(size_t)p * b.bstride + min(cb0 + tid, nbt)];
+  if (tid <= FIN_BPC) {
+    const uint32_t bo = b.boff[(size_t)p * b.bstride + min(cb0 + tid, nbt)];
+    sbo[tid] = bo;
+    sso[tid] = b.slab ? fn->soff[min(cb0 + tid, nbt)] : bo;
+  }
   __syncthreads();
   if (fb) return;
-  const uint32_t* pi0 = b.pidx + (size_t)p * M;
-  const uint64_t* pk0 = b.pkey + (size_t)p * M;
+  const uint32_t* pi0 = b.pidx + (size_t)p * b.pstride;
+  const uint64_t* pk0 = b.pkey + (size_t)p * b.pstride;
   const int sh = 31 - __clz(nsub);
 #pragma unroll 1
   for (int q = 0; q < FIN_BPC; ++q) {
     const int cb = cb0 + q;
     if (cb >= nbt) break;
-    const uint32_t B0 = sbo[q], n = sbo[q + 1] - B0;
+    const uint32_t B0 = sbo[q], n = sbo[q + 1] - B0, S0 = sso[q];
     const FineFn ff = make_fine<NFINE>(fn, cb, nsub);
 #if B200REF_FIN_PF != 0
     if (tid >= FIN_NT - 32 && q + 1 < FIN_BPC && cb + 1 < nbt) {
       // the last warp (the one most often idle in a bucket's tail) issues one prefetch per 128-byte line of
       // the next bucket's keys and positions, and of its bucket function
       const uint32_t lane = tid & 31;
-      const uint32_t nB0 = sbo[q + 1], nn = min(sbo[q + 2] - nB0, (uint32_t)CAP1);
-      const uintptr_t ka = (uintptr_t)(pk0 + nB0), ke = ka + (size_t)nn * 8;
-      const uintptr_t ia = (uintptr_t)(pi0 + nB0), ie = ia + (size_t)nn * 4;
+      const uint32_t nS0 = sso[q + 1], nn = min(sbo[q + 2] - sbo[q + 1], (uint32_t)CAP1);
+      const uintptr_t ka = (uintptr_t)(pk0 + nS0), ke = ka + (size_t)nn * 8;
+      const uintptr_t ia = (uintptr_t)(pi0 + nS0), ie = ia + (size_t)nn * 4;
       const uint32_t nlk = nn ? (uint32_t)(((ke - 1) >> 7) - (ka >> 7)) + 1u : 0u;
       const uint32_t nli = nn ? (uint32_t)(((ie - 1) >> 7) - (ia >> 7)) + 1u : 0u;
       for (uint32_t l = lane; l < nlk + nli; l += 32)
@@ -1076,14 +1348,14 @@ __global__ void __launch_bounds__(FIN_NT, B200REF_FIN_OCC) k_finish(uint32_t M, 
       uint32_t* oc = b.kcode + (size_t)p * M + B0;
       double* orank = fo.rank ? fo.rank + (size_t)p * M : nullptr;
       for (uint32_t e = tid; e < n; e += FIN_NT) {
-        const uint32_t pos = pi0[B0 + e];
-        ok[e] = pk0[B0 + e];
+        const uint32_t pos = pi0[S0 + e];
+        ok[e] = pk0[S0 + e];
         oi[e] = pos | TIED_BIT;
         oc[e] = kc;
         if (orank) orank[pos] = (double)(kc + 1u) * 0.5;
       }
     } else if (wanted && n != 0 && n <= (uint32_t)CAP1) {  // oversize buckets: k_finish_big
-        finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false, false>(sm, ff, B0, n, M, p, b, fo);
+        finish_bucket<FIN_NT, NFINE, CAP1, FIN_IPT, false, false>(sm, ff, B0, S0, n, M, p, b, fo);
       __syncthreads();
     }
   }
@@ -1103,9 +1375,10 @@ __global__ void __launch_bounds__(FINB_NT) k_finish_big(uint32_t M, BucketBufs b
     if (b.fallback[p]) continue;
     const uint32_t B0 = b.boff[(size_t)p * b.bstride + cb];
     const uint32_t n = b.boff[(size_t)p * b.bstride + cb + 1] - B0;
+    const uint32_t S0 = b.slab ? b.fn[p].soff[cb] : B0;
     B200REF_CHECK(q < b.biglist_cap && n <= (uint32_t)CAPBIG && B0 + n <= M, "k_finish_big: list entry out of range");
     __syncthreads();
-    finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true, true>(sm, make_fine<NFINE_BIG>(b.fn + p, cb, nsub), B0, n, M, p, b, fo);
+    finish_bucket<FINB_NT, NFINE_BIG, CAPBIG, 1, true, true>(sm, make_fine<NFINE_BIG>(b.fn + p, cb, nsub), B0, S0, n, M, p, b, fo);
   }
 }
 

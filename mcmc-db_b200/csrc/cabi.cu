@@ -128,6 +128,15 @@ inline int fold_bin_shift(int64_t M) {
   return std::max(B200REF_BIN_MIN_SHIFT, lg - 5);
 }
 
+// Single-pass partition (k_part1, narrow path): every coarse bucket owns a slack-padded slab of the parameter's
+// record region (capacities: k_sample).  0 at compile time = the two-pass partition (k_bhist + k_bscan + k_partition).
+#ifndef B200REF_SINGLE_PASS
+#define B200REF_SINGLE_PASS 1
+#endif
+inline bool use_slabs(int64_t M) { return B200REF_SINGLE_PASS != 0 && choose_sub(M) == 1; }
+// records of one parameter's slab region: 3 x the mean per bucket + 64 (k_sample), + room for pure buckets
+inline size_t slab_records(int64_t M) { return use_slabs(M) ? (size_t)5 * (size_t)M + 32768 : (size_t)M; }
+
 // Workspace carve-up for one batch of PB parameters with M pooled draws each.
 struct Layout {
   size_t ztab, zodd, flag, header;  // shared part
@@ -144,9 +153,10 @@ struct Layout {
     header = o;
     size_t b = 0;
     const size_t n = (size_t)PB * (size_t)M;
-    pkey = b; b += up(n * 8);
+    const size_t nrec = (size_t)PB * slab_records(M);  // partitioned records (slack-padded slabs on the single-pass path)
+    pkey = b; b += up(nrec * 8);
     skey = b; b += up(n * 8);
-    pidx = b; b += up(n * 4);
+    pidx = b; b += up(nrec * 4);
     sidx = b; b += up(n * 4);
     kcode = b; b += up(n * 4);
     zz = b; b += diag ? up(n * 16) : 0;
@@ -155,9 +165,10 @@ struct Layout {
     bcur = b; b += binned ? up((size_t)PB * 32 * 4) : 0;
     fn = b; b += up((size_t)PB * sizeof(BucketFn));
     const bool wide = choose_sub(M) > 1;  // long chains: sub-bucketed coarse buckets, no per-chunk counts
-    cnt = b; b += wide ? 0 : up((size_t)PB * nchunks * NB1_MAX * 4);
+    const bool slabs = use_slabs(M);
+    cnt = b; b += (wide || slabs) ? 0 : up((size_t)PB * nchunks * NB1_MAX * 4);
     boff = b; b += up((size_t)PB * (wide ? NBW_MAX + 1 : NB1_MAX + 1) * 4);
-    cur = b; b += wide ? up((size_t)PB * NBW_MAX * 4) : 0;
+    cur = b; b += wide ? up((size_t)PB * NBW_MAX * 4) : (slabs ? up((size_t)PB * NB1_MAX * 4) : 0);
     spart = b; b += up((size_t)PB * nchunks * 2 * 8);
     fallback = b; b += up((size_t)PB);
     nfb = b; b += up(sizeof(int));
@@ -347,6 +358,7 @@ int ensure_kernel_attributes() {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     };
     set((const void*)k_partition, sizeof(PartSmem));
+    set((const void*)k_part1, sizeof(Part1Smem));
     set((const void*)k_finish, sizeof(FinSmemSmall));
     set((const void*)k_finish_big, sizeof(FinSmemBig));
     set((const void*)k_moments0, sizeof(Mo0Smem));
@@ -458,6 +470,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
   for (int i = 0; i < nq; ++i) qa.q[i] = q_host[i];
   const int nb1 = choose_nb1(M), nsub = choose_sub(M);
   const bool wide = nsub > 1;
+  const bool slabs = use_slabs(M);
 
   for (int64_t p0 = 0; p0 < P; p0 += PBmax) {
     const int PB = (int)std::min<int64_t>(PBmax, P - p0);
@@ -478,6 +491,9 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     bb.flag = flag;
     bb.pkey = (uint64_t*)(wb + L.pkey);
     bb.pidx = (uint32_t*)(wb + L.pidx);
+    bb.pstride = slab_records(M);
+    bb.slab = slabs ? 1 : 0;
+    bb.slab_cap = (uint32_t)std::min<size_t>(slab_records(M), 0x7fffffffu);
     bb.skey = (uint64_t*)(wb + L.skey);
     bb.sidx = (uint32_t*)(wb + L.sidx);
     bb.kcode = (uint32_t*)(wb + L.kcode);
@@ -490,7 +506,12 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     // ---- distribution sort: sample -> histogram -> offsets -> partition -> on-chip finish ----
     const dim3 gc(L.nchunks, PB);
     LAUNCH(K_SAMPLE, st, k_sample<<<PB, 512, 0, st>>>(xb, (uint32_t)M, bb));
-    if (!wide) {
+    if (slabs) {
+      // single pass: the partition itself counts (one global atomic per (chunk, bucket) reserves the run)
+      CUDA_TRY(cudaMemsetAsync(bb.cur, 0, (size_t)PB * NB1_MAX * 4, st));
+      LAUNCH(K_PARTITION, st, k_part1<<<gc, P1_NT, sizeof(Part1Smem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
+      LAUNCH(K_BSCAN, st, k_bscan1<<<PB, NB1_MAX, 0, st>>>((uint32_t)M, L.nchunks, bb));
+    } else if (!wide) {
       LAUNCH(K_BHIST, st, k_bhist<<<gc, PART_NT, 0, st>>>(xb, (uint32_t)M, L.nchunks, bb));
       LAUNCH(K_BSCAN, st, k_bscan<<<PB, NB1_MAX, 0, st>>>((uint32_t)M, L.nchunks, bb));
     } else {
@@ -527,7 +548,7 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     rb.zodd = zodd;
     rb.flag = flag;
     const dim3 gt(L.ntiles, PB);
-    {
+    auto launch_lsd = [&]() -> int {
       // while per-kernel timing is on, the fallback runs on the main stream so that every
       // event pair brackets one kernel alone (overlapped launches would share their interval)
       SideStream& ss = side_stream(slot);
@@ -541,11 +562,17 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
         LAUNCH(K_RADIX, fs, k_radix_pass<false><<<fbg, SORT_NT, 0, fs>>>(xb, (uint32_t)M, pass, sb));
       LAUNCH(K_RANKC, fs, k_rank_codes<<<dim3(L.ntiles, std::min(PB, 8)), RANK_NT, 0, fs>>>(rb, (uint32_t)M, rank_b_batch));
       CUDA_TRY(cudaEventRecord(ss.join, fs));
+      return B200REF_OK;
+    };
+    if (!slabs) {
+      // (two-pass partition: the list is known after k_bscan, the fallback overlaps k_partition / k_finish)
+      const int rc = launch_lsd();
+      if (rc) return rc;
+      if (!wide)
+        LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
+      else
+        LAUNCH(K_PARTITION, st, k_partition_w<<<gc, PART_NT, sizeof(WideSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
     }
-    if (!wide)
-      LAUNCH(K_PARTITION, st, k_partition<<<gc, PART_NT, sizeof(PartSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
-    else
-      LAUNCH(K_PARTITION, st, k_partition_w<<<gc, PART_NT, sizeof(WideSmem), st>>>(xb, (uint32_t)M, L.nchunks, bb));
     FinishOut fin;
     memset(&fin, 0, sizeof(fin));
     fin.rank = rank_b_batch;
@@ -564,6 +591,12 @@ int run(const double* x, int64_t P, int64_t C, int64_t N, const double* q_host, 
     LAUNCH(K_FINISH, st, k_finish<<<dim3((nb1 * nsub + FIN_BPC - 1) / FIN_BPC, PB), FIN_NT, sizeof(FinSmemSmall), st>>>((uint32_t)M, nsub, nb1 * nsub, bb, fin));
     fin.npos = 0;  // oversize buckets are always ranked
     LAUNCH(K_FINISHB, st, k_finish_big<<<std::min(PB * 4, FALLBACK_GRID), FINB_NT, sizeof(FinSmemBig), st>>>((uint32_t)M, bb, fin));
+    if (slabs) {
+      // the LSD path works in the dense [p][M] views of pkey / pidx, which overlap other parameters' slabs: it
+      // starts when the finish kernels have read them
+      const int rc = launch_lsd();
+      if (rc) return rc;
+    }
     CUDA_TRY(cudaStreamWaitEvent(st, side_stream(slot).join, 0));
 
     PrepOut po;

@@ -47,6 +47,36 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                       \
   } while (0)
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// zz [rows][8 pairs] as a 2-D fp64 tensor (row = 16 doubles = 128 B = one swizzle row); box = M2_BOX rows: k_moments0t
+int make_map_pairs(CUtensorMap* map, const void* zz, uint64_t rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(B200REF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {16, rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {16, (cuuint32_t)M2_BOX};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(zz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200REF_ERR_CUDA, "cuTensorMapEncodeTiled (score pairs) failed with code %d", (int)r);
+  return B200REF_OK;
+}
+
 // ---- optional per-kernel timing (bench.py's roofline block): CUDA events recorded on the
 // launching stream around every kernel while enabled.
 enum KernelId { K_ZTABLE, K_SAMPLE, K_BHIST, K_BSCAN, K_PARTITION, K_FINISH, K_FINISHB, K_HIST0, K_RADIX, K_RANKC, K_PREP,
@@ -132,6 +162,10 @@ inline int fold_bin_shift(int64_t M) {
 // record region (capacities: k_sample).  0 at compile time = the two-pass partition (k_bhist + k_bscan + k_partition).
 #ifndef B200REF_SINGLE_PASS
 #define B200REF_SINGLE_PASS 1
+#endif
+// Round 0 of the chain statistics by the tile variant (k_moments0t) whenever the chain length allows (N % 8 == 0)
+#ifndef B200REF_MOMENTS_TILE
+#define B200REF_MOMENTS_TILE 1
 #endif
 inline bool use_slabs(int64_t M) { return B200REF_SINGLE_PASS != 0 && choose_sub(M) == 1; }
 // records of one parameter's slab region: 3 x the mean per bucket + 64 (k_sample), + room for pure buckets
@@ -362,6 +396,7 @@ int ensure_kernel_attributes() {
     set((const void*)k_finish, sizeof(FinSmemSmall));
     set((const void*)k_finish_big, sizeof(FinSmemBig));
     set((const void*)k_moments0, sizeof(Mo0Smem));
+    set((const void*)k_moments0t, M2_SMEM);
     set((const void*)k_ess_rounds, sizeof(RoundsSmem));
     set((const void*)k_decide0, 3 * (size_t)MAX_CHAINS * sizeof(double));  // 96 KB at the advertised 4096 chains
     attr_err[dev] = e;
@@ -395,7 +430,19 @@ int launch_chain_stats(const double2* zz, int PB, int64_t C, int64_t N, char* wb
     // units per CTA: about MO_CTA_TILES sub-tiles of work behind one exposed first copy
     const uint32_t upc = std::max<uint32_t>(1u, MO_CTA_TILES / g.tpu);
     const unsigned gx = (unsigned)((C * g.nunits + upc - 1) / upc);
-    LAUNCH(K_CHAIN, st, k_moments0<<<dim3(gx, PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, upc, cs.part));
+    if (B200REF_MOMENTS_TILE != 0 && (N % 8) == 0 && ((uintptr_t)zz % 128) == 0) {
+      // tile variant: 2-D TMA into swizzled landing buffers, both kinds per thread (no de-interleave pass)
+      CUtensorMap map;
+      const int rc = make_map_pairs(&map, zz, (uint64_t)PB * (uint64_t)C * (uint64_t)(N / 8));
+      if (rc) return rc;
+      // every warp of a CTA owns whole units: about 32 tiles (of 32 rows) of work behind one exposed first copy
+      const uint32_t upw = std::max<uint32_t>(1u, 32u / (g.tpu * (MO_SUB / 8 / M2_ROWS)));
+      const uint32_t upc_t = M2_NW * upw;
+      const unsigned gxt = (unsigned)((C * g.nunits + upc_t - 1) / upc_t);
+      LAUNCH(K_CHAIN, st, k_moments0t<<<dim3(gxt, PB), M2_NT, M2_SMEM, st>>>(map, g, upc_t, cs.part));
+    } else {
+      LAUNCH(K_CHAIN, st, k_moments0<<<dim3(gx, PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, upc, cs.part));
+    }
   }
   LAUNCH(K_DECIDE, st, k_decide0<<<2 * PB, DEC_NT, 3 * (size_t)C * sizeof(double), st>>>(zz, g, PB, cs));
   if ((uint32_t)N > 1u + LAGB) {
@@ -1141,22 +1188,6 @@ int b200ref_synth_fill_f64(double* x, int64_t p0, int64_t P, int64_t C, int64_t 
 // GLM log-density (logistic regression) on the tcgen05 tensor cores -- see csrc/glm.cuh
 // ---------------------------------------------------------------------------------------------
 namespace {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
 
 // [rows][cols] bf16 row-major; box = 64 columns (128 B, one swizzle row) x box_rows rows
 int make_map_bf16(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {

@@ -286,6 +286,219 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restric
   }
 }
 
+// ---------------------------------------------------------------- round 0, tile variant (N % 8 == 0)
+// The same partial sums as k_moments0, without the de-interleave pass, without block barriers and with a quarter of
+// the reductions.  zz is viewed as a 2-D fp64 tensor of rows of 8 {z_bulk, z_folded} pairs (128 B).  Every WARP owns
+// whole units (runs of one chain): a tile of 32 rows + 2 halo rows arrives by one 2-D TMA copy (cp.async.bulk.tensor,
+// SASS UTMALDG) in the 128-byte swizzle, so that lane t's 16-byte reads of row t (and of rows t + 1, t + 2 for the lag
+// partners) are bank-conflict free straight from the landing buffer: no staging copy.  A lane keeps its 8 draws of
+// BOTH kinds in registers and accumulates 2 x 16 lag products against the 24 draws that follow (256 DFMA per
+// 24 LDS.128).  Three landing buffers per warp, two copies always in flight; the warps of a CTA never synchronise
+// with each other, and a unit's totals are reduced inside its warp only.  Units, partial-sum layout and the decision
+// kernel are those of k_moments0.
+constexpr int M2_NT = 128;                       // threads per CTA (4 independent warps)
+constexpr int M2_NW = M2_NT / 32;
+constexpr int M2_ROWS = 32;                      // rows per tile = lanes
+constexpr int M2_BOX = M2_ROWS + 2;              // + 2 halo rows: the 16 draws after the tile's last one
+constexpr int M2_TILE_BYTES = M2_BOX * 128;
+constexpr int M2_STAGE = ((M2_TILE_BYTES + 1023) / 1024) * 1024;  // landing buffers are 1024-byte aligned (swizzle atom)
+#ifndef B200REF_M2_NST
+#define B200REF_M2_NST 3
+#endif
+constexpr int M2_NST = B200REF_M2_NST;
+#ifndef B200REF_M2_OCC
+#define B200REF_M2_OCC 3
+#endif
+constexpr size_t M2_SMEM = 1024 + (size_t)M2_NW * M2_NST * M2_STAGE + (size_t)M2_NW * M2_NST * 8;
+
+// pair `k` (0..7) of row `r` of a landing buffer (128-byte swizzle: 16-byte chunk index ^ (row & 7)).
+// (`tile` is the buffer's 32-bit shared-window address: explicit ld.shared, the rounded-up base pointer is generic)
+__device__ __forceinline__ double2 m2_pair(uint32_t tile, uint32_t r, uint32_t k) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(tile + r * 128u + ((k ^ (r & 7u)) << 4)));
+  return v;
+}
+
+// v[8] per lane -> lane l returns the warp total of v[l & 7]
+__device__ __forceinline__ double warp_reduce_8(double (&v)[8]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const double a = v[k], b = v[k + s];
+      const double keep = up ? b : a;
+      const double send = up ? a : b;
+      v[k] = keep + __shfl_xor_sync(FULL, send, s);
+    }
+  }
+  double t = v[0] + __shfl_xor_sync(FULL, v[0], 8);
+  return t + __shfl_xor_sync(FULL, t, 16);
+}
+
+__global__ void __launch_bounds__(M2_NT, B200REF_M2_OCC) k_moments0t(const __grid_constant__ CUtensorMap map, ChainGeom g, uint32_t upc,
+                                                                     double* part) {
+  extern __shared__ __align__(128) unsigned char mo_smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mo_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int p = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  unsigned char* wbase = base + (size_t)wp * M2_NST * M2_STAGE;              // this warp's landing buffers
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)M2_NW * M2_NST * M2_STAGE) + wp * M2_NST;
+  const uint32_t wbase_s = smem_u32(wbase);
+  const uint32_t nu = g.C * g.nunits;
+  const uint32_t unit0 = blockIdx.x * upc + wp, unit1 = min(blockIdx.x * upc + upc, nu);  // this warp: unit0, unit0 + 4, ...
+  const uint32_t Rc = g.N >> 3;                          // rows per chain
+  const uint32_t prow0 = (uint32_t)p * g.C * Rc;         // first row of this parameter
+  if (lane == 0) {
+    for (int s = 0; s < M2_NST; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  // rows [ra, rb) of chain c for a unit
+  auto unit_rows = [&](uint32_t unit, uint32_t& c, uint32_t& ra, uint32_t& rb) {
+    c = unit / g.nunits;
+    uint32_t a, b;
+    unit_range(g, unit % g.nunits, a, b);
+    ra = a >> 3;
+    rb = b >> 3;
+  };
+  // producer cursor (lane 0): the next tile to request
+  uint32_t iu = unit0, it_ = 0, issued = 0;
+  auto issue_next = [&]() {  // lane 0 only
+    while (iu < unit1) {
+      uint32_t c, ra, rb;
+      unit_rows(iu, c, ra, rb);
+      const uint32_t nt = (rb - ra + M2_ROWS - 1) / M2_ROWS;
+      if (it_ < nt) {
+        const uint32_t st = issued % M2_NST;
+        fence_proxy_async();  // earlier generic reads of this landing buffer are ordered before the async-proxy writes
+        mbar_expect_tx(&full[st], (uint32_t)M2_TILE_BYTES);
+        tma_load_2d(wbase + (size_t)st * M2_STAGE, &map, &full[st], 0, (int)(prow0 + c * Rc + ra + it_ * M2_ROWS));
+        ++it_;
+        ++issued;
+        return;
+      }
+      iu += M2_NW;
+      it_ = 0;
+    }
+  };
+  if (lane == 0)
+    for (int s = 0; s < M2_NST; ++s) issue_next();
+  const uint32_t half = g.half;
+  uint32_t seq = 0;  // tiles consumed so far by this warp
+  for (uint32_t unit = unit0; unit < unit1; unit += M2_NW) {
+    uint32_t c, ra, rb;
+    unit_rows(unit, c, ra, rb);
+    const uint32_t a = ra << 3, b = rb << 3;
+    const bool has1 = a < half, has2 = b > half && max(a, half) < 2 * half;
+    const uint32_t pos2 = max(a, half);
+    double accb[LAGB], accf[LAGB];
+#pragma unroll
+    for (int l = 0; l < LAGB; ++l) { accb[l] = 0.0; accf[l] = 0.0; }
+    double hs[8];  // s1b q1b s2b q2b s1f q1f s2f q2f
+#pragma unroll
+    for (int l = 0; l < 8; ++l) hs[l] = 0.0;
+    double2 f1 = make_double2(0.0, 0.0), f2 = make_double2(0.0, 0.0);
+    bool d1b = false, d2b = false, d1f = false, d2f = false;
+    const uint32_t ntile = (rb - ra + M2_ROWS - 1) / M2_ROWS;
+    for (uint32_t ti = 0; ti < ntile; ++ti, ++seq) {
+      const uint32_t st = seq % M2_NST;
+      const uint32_t tile = wbase_s + st * (uint32_t)M2_STAGE;
+      mbar_wait(&full[st], (seq / M2_NST) & 1u);
+      const uint32_t row0 = ra + ti * M2_ROWS;  // chain row of the tile's first row
+      if (ti == 0 && has1) f1 = m2_pair(tile, 0, 0);
+      if (has2 && (pos2 >> 3) >= row0 && (pos2 >> 3) < row0 + M2_ROWS) f2 = m2_pair(tile, (pos2 >> 3) - row0, pos2 & 7u);
+      const uint32_t rc = row0 + lane;          // this lane's row of the chain
+      if (rc < rb) {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = m2_pair(tile, lane, k);
+        // partners inside the row: lags 1 .. 7
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+#pragma unroll
+          for (int s = 0; s < j; ++s) {
+            accb[j - s - 1] = fma(v[s].x, v[j].x, accb[j - s - 1]);
+            accf[j - s - 1] = fma(v[s].y, v[j].y, accf[j - s - 1]);
+          }
+        }
+        if (rc + 1 < Rc) {  // next row (same chain): lags 1 .. 15
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double2 w = m2_pair(tile, lane + 1, j);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              accb[8 + j - s - 1] = fma(v[s].x, w.x, accb[8 + j - s - 1]);
+              accf[8 + j - s - 1] = fma(v[s].y, w.y, accf[8 + j - s - 1]);
+            }
+          }
+        }
+        if (rc + 2 < Rc) {  // the row after: lags 9 .. 16
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const double2 w = m2_pair(tile, lane + 2, j);
+#pragma unroll
+            for (int s = j; s < 8; ++s) {
+              accb[16 + j - s - 1] = fma(v[s].x, w.x, accb[16 + j - s - 1]);
+              accf[16 + j - s - 1] = fma(v[s].y, w.y, accf[16 + j - s - 1]);
+            }
+          }
+        }
+        // per-half sums, sums of squares and "some draw differs from the half's first one" (bit patterns: scores are
+        // table entries, equal values are equal bits)
+        const uint32_t g0 = rc << 3;
+        const bool in1 = g0 + 8 <= half, in2 = g0 >= half && g0 + 8 <= 2 * half;
+        if (in1 || in2) {
+          const long long rb_ = __double_as_longlong(in1 ? f1.x : f2.x), rf_ = __double_as_longlong(in1 ? f1.y : f2.y);
+          double lsb = 0.0, lqb = 0.0, lsf = 0.0, lqf = 0.0;
+          bool ldb = false, ldf = false;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            lsb += v[s].x; lqb = fma(v[s].x, v[s].x, lqb); ldb |= (__double_as_longlong(v[s].x) != rb_);
+            lsf += v[s].y; lqf = fma(v[s].y, v[s].y, lqf); ldf |= (__double_as_longlong(v[s].y) != rf_);
+          }
+          if (in1) { hs[0] += lsb; hs[1] += lqb; d1b |= ldb; hs[4] += lsf; hs[5] += lqf; d1f |= ldf; }
+          else     { hs[2] += lsb; hs[3] += lqb; d2b |= ldb; hs[6] += lsf; hs[7] += lqf; d2f |= ldf; }
+        } else {
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            const uint32_t gi = g0 + s;
+            if (gi < half) {
+              hs[0] += v[s].x; hs[1] = fma(v[s].x, v[s].x, hs[1]); d1b |= (v[s].x != f1.x);
+              hs[4] += v[s].y; hs[5] = fma(v[s].y, v[s].y, hs[5]); d1f |= (v[s].y != f1.y);
+            } else if (gi < 2 * half) {
+              hs[2] += v[s].x; hs[3] = fma(v[s].x, v[s].x, hs[3]); d2b |= (v[s].x != f2.x);
+              hs[6] += v[s].y; hs[7] = fma(v[s].y, v[s].y, hs[7]); d2f |= (v[s].y != f2.y);
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane has read the landing buffer: it can take the next copy
+      if (lane == 0) issue_next();
+    }
+    // unit totals (fixed order): halving reduces inside the warp, written straight to the unit's partial sums
+    const double totb = warp_reduce_16(accb);
+    const double totf = warp_reduce_16(accf);
+    const double toth = warp_reduce_8(hs);
+    const bool w1b = __any_sync(FULL, d1b), w2b = __any_sync(FULL, d2b), w1f = __any_sync(FULL, d1f), w2f = __any_sync(FULL, d2f);
+    double* pb = part + (((size_t)p * nu + unit) * 2 + 0) * MO_VALS;
+    double* pf = pb + MO_VALS;
+    if (lane < LAGB) { pb[lane] = totb; pf[lane] = totf; }
+    // lane l (< 8) holds hs[l]: s1b q1b s2b q2b | s1f q1f s2f q2f
+    if (lane < 4) pb[16 + (lane >> 1) * 5 + (lane & 1)] = toth;
+    else if (lane < 8) pf[16 + ((lane - 4) >> 1) * 5 + (lane & 1)] = toth;
+    if (lane == 8) {
+      pb[18] = f1.x; pb[19] = w1b ? 1.0 : 0.0; pb[20] = has1 ? 1.0 : 0.0;
+      pb[23] = f2.x; pb[24] = w2b ? 1.0 : 0.0; pb[25] = has2 ? 1.0 : 0.0;
+    }
+    if (lane == 9) {
+      pf[18] = f1.y; pf[19] = w1f ? 1.0 : 0.0; pf[20] = has1 ? 1.0 : 0.0;
+      pf[23] = f2.y; pf[24] = w2f ? 1.0 : 0.0; pf[25] = has2 ? 1.0 : 0.0;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- later rounds: one kind, lags t0 .. t0+31
 // One unit = (listed item, chain, unit of the chain), 256 threads.  Two TMA-staged tiles per sub-tile: first factors y[i] and
 // second factors y[i + t0 + ...]; threads 0-127 accumulate lags t0..t0+15, threads 128-255 lags

@@ -327,6 +327,73 @@ def test_heavy_ties_stay_on_the_fast_path(B):
     assert ms["half_zero"] < 3.0 * ms["cont"], ms
 
 
+def test_slab_overflow_takes_the_lsd_path(B):
+    """Single-pass partition: a repeated value that the strided sample never sees (it sits on every position the sample
+    does not read) lands in an ordinary coarse bucket, whose slab it overflows; the parameter must be listed for the LSD
+    path and come out exact.  A neighbouring well-behaved parameter in the same batch must be untouched."""
+    rng = np.random.default_rng(91)
+    c, n = 8, 8192
+    m = c * n
+    nb1 = 1
+    while nb1 < 256 and m > nb1 * 768:
+        nb1 *= 2
+    s = min(nb1 * 16, m)
+    sampled = np.array([((2 * j + 1) * m) // (2 * s) for j in range(s)])
+    evil = np.full(m, 0.125)
+    evil[sampled] = rng.standard_normal(s)
+    good = rng.standard_normal(m)
+    x = np.stack([good.reshape(c, n), evil.reshape(c, n), good.reshape(c, n) * 2.0 + 1.0])
+    d = B.diagnostics_batch(x)
+    for i in range(3):
+        want = O.diagnostics_param(x[i])
+        for k in ("rhat", "ess_bulk", "ess_tail"):
+            assert close(float(d[k][i].item()), want[k], TOL), (i, k, float(d[k][i].item()), want[k])
+        ns = O.numpy_stats(x[i].reshape(-1))
+        for j, q in enumerate(("q5", "q50", "q95")):
+            assert float(d["quantiles"][i, j].item()) == ns[q], (i, q)
+    r = B.ranks_batch(x[1][None])
+    rank, z = O.rank_normalize(x[1])
+    assert np.array_equal(r["avg_rank"][0].cpu().numpy(), rank)
+    assert np.array_equal(r["z"][0].cpu().numpy(), z)
+
+
+def test_many_discrete_values_in_slabs(B):
+    """Columns rounded to a grid (every 101st parameter of the synthetic workload): dozens of pure buckets whose slabs
+    are sized from the sample, next to ordinary buckets that hold a few grid points each."""
+    rng = np.random.default_rng(92)
+    c, n = 16, 10_000
+    for scale, name in ((0.25, "grid_150_values"), (4.0, "grid_2400_values")):
+        x = np.round(rng.standard_normal((c, n)) * scale, 2)
+        r = B.ranks_batch(x[None])
+        rank, z = O.rank_normalize(x)
+        rank_f, z_f = O.rank_normalize(O.fold_chains(x))
+        assert np.array_equal(r["avg_rank"][0].cpu().numpy(), rank), name
+        assert np.array_equal(r["avg_rank_folded"][0].cpu().numpy(), rank_f), name
+        assert np.array_equal(r["z"][0].cpu().numpy(), z) and np.array_equal(r["z_folded"][0].cpu().numpy(), z_f), name
+        _check_vs_oracle(B, x, name)
+
+
+@pytest.mark.parametrize("n", [8, 16, 24, 40, 1000, 1016, 2048, 2056, 4096, 6152, 16392, 40_000])
+def test_round0_tile_variant_chain_lengths(B, n):
+    """Chain lengths that are multiples of 8 take the tile variant of round 0 (k_moments0t: 2-D TMA into swizzled
+    landing buffers, both kinds per thread): tile and unit boundaries, a split point inside a row (n = 1000, 1016,
+    6152), chains shorter than the lag window, sticky chains that go on into the later rounds -- against the oracle,
+    truncation lags compared for equality."""
+    from scipy.signal import lfilter
+
+    rng = np.random.default_rng(1000 + n)
+    c = 5
+    for phi in (0.0, 0.9):
+        x = lfilter([math.sqrt(1 - phi * phi)], [1.0, -phi], rng.standard_normal((c, n)), axis=1)
+        x[2] += 0.3  # unequal chain means: between-chain variance in R-hat and in var_hat
+        _check_vs_oracle(B, x, f"n={n} phi={phi}")
+    if n >= 16:
+        x = rng.standard_normal((c, n))
+        x[:, : n // 2] = 1.5  # constant first halves: zero within-half variance must come out exactly
+        x[1] = -2.0           # and one constant chain
+        _check_vs_oracle(B, x, f"n={n} constant halves")
+
+
 def test_ragged_chains_follow_the_reference(B):
     """Chains of different lengths (fixture from the unmodified reference, `make_ragged_golden.py`): pooled ranks over
     all draws, each chain split at its own midpoint, every (split) chain truncated to the shortest one."""

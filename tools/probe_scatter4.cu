@@ -1,0 +1,143 @@
+// Hardware probe: 16-byte scatter of {z_bulk, z_folded} pairs to random positions of a parameter's 4 MB row --
+// LSU path (st.global.cs.v2.f64, one L1 wavefront per store) against the TMA path
+// (cp.async.bulk.tensor.2d ... tile::scatter4: four 16-byte rows per instruction, staged in shared memory).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 tools/probe_scatter4.cu -o build/probe/scatter4
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("ERR %s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mixh(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+constexpr int NT = 128, IPT = 8, TILE = NT * IPT;
+
+// MODE 0: direct scattered 16-byte stores.  MODE 1: scatter4 from 128-byte aligned groups.  MODE 2: from packed
+// 64-byte groups.  MODE 3: as 1 but only one lane in four issues (four scatter4 each): issue-rate test.
+template <int MODE>
+__global__ void __launch_bounds__(NT) k_scatter(const __grid_constant__ CUtensorMap map, double2* zz, uint32_t M, uint32_t ntiles) {
+  const uint32_t p = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  const size_t pbase = (size_t)p * M;
+  uint32_t pos[IPT];
+  // a bijection of [0, M) (M a power of two): every position of the row is written exactly once, as in k_fold
+#pragma unroll
+  for (int it = 0; it < IPT; ++it) {
+    uint32_t x = tile * TILE + it * NT + tid;
+    x = (x * 0x9E3779B1u + p * 0x85EBCA6Bu) & (M - 1);
+    x ^= x >> 9;
+    x = (x * 0xC2B2AE35u) & (M - 1);
+    x ^= x >> 7;
+    pos[it] = x;
+  }
+  if constexpr (MODE == 0) {
+#pragma unroll
+    for (int it = 0; it < IPT; ++it) __stcs(&zz[pbase + pos[it]], make_double2((double)pos[it], (double)p));
+    return;
+  }
+  __shared__ __align__(128) unsigned char stage[TILE / 4 * 128];
+  constexpr uint32_t GSTRIDE = (MODE == 2) ? 64u : 128u;
+  // thread t owns groups 2t and 2t+1 (4 pairs each): its own 8 pairs
+#pragma unroll
+  for (int it = 0; it < IPT; ++it) {
+    const uint32_t grp = 2 * tid + (it >> 2);
+    *reinterpret_cast<double2*>(stage + grp * GSTRIDE + (it & 3) * 16) = make_double2((double)pos[it], (double)p);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (MODE == 3) __syncwarp();
+  const uint32_t rb = (uint32_t)pbase;  // rows are global pair indices (fits: P * M < 2^31 here)
+  if (MODE != 3) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const uint32_t src = smem_u32(stage + (2 * tid + g) * GSTRIDE);
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile::scatter4.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                   ::"l"(&map), "r"(0), "r"(rb + pos[4 * g]), "r"(rb + pos[4 * g + 1]), "r"(rb + pos[4 * g + 2]), "r"(rb + pos[4 * g + 3]),
+                   "r"(src)
+                   : "memory");
+    }
+  } else {
+    // positions travel through shared memory to the issuing lanes
+    __shared__ uint32_t spos[TILE];
+#pragma unroll
+    for (int it = 0; it < IPT; ++it) spos[(2 * tid + (it >> 2)) * 4 + (it & 3)] = pos[it];
+    __syncthreads();
+    if ((tid & 3) == 0) {
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t grp = 2 * tid + g;
+        const uint32_t src = smem_u32(stage + grp * GSTRIDE);
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile::scatter4.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                     ::"l"(&map), "r"(0), "r"(rb + spos[grp * 4]), "r"(rb + spos[grp * 4 + 1]), "r"(rb + spos[grp * 4 + 2]),
+                     "r"(rb + spos[grp * 4 + 3]), "r"(src)
+                     : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int MODE>
+void run(const char* name, const CUtensorMap& map, double2* zz, uint32_t P, uint32_t M) {
+  const uint32_t ntiles = M / TILE;
+  CK(cudaMemset(zz, 0, (size_t)P * M * 16));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  k_scatter<MODE><<<dim3(ntiles, P), NT>>>(map, zz, M, ntiles);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(a));
+  const int reps = 5;
+  for (int r = 0; r < reps; ++r) k_scatter<MODE><<<dim3(ntiles, P), NT>>>(map, zz, M, ntiles);
+  CK(cudaEventRecord(b));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  ms /= reps;
+  // verify: every entry is 0 (never hit) or {its own position, its parameter}
+  const size_t n = (size_t)4 * M;
+  double2* h = (double2*)malloc(n * 16);
+  CK(cudaMemcpy(h, zz + (size_t)(P - 4) * M, n * 16, cudaMemcpyDeviceToHost));
+  size_t bad = 0, hit = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double px = (double)(i % M), pp = (double)(P - 4 + i / M);
+    if (h[i].x == px && h[i].y == pp) ++hit; else ++bad;
+  }
+  free(h);
+  const double pairs = (double)P * M;
+  printf("%-34s %8.3f ms  %7.2f Gpairs/s  %6.3f pairs/cycle/SM (1.965 GHz, 148 SMs)  verify: hit %zu bad %zu\n", name, ms,
+         pairs / ms * 1e-6, pairs / (ms * 1e-3) / (148 * 1.965e9), hit, bad);
+}
+
+int main(int argc, char** argv) {
+  const uint32_t P = 256, M = 262144;
+  double2* zz;
+  CK(cudaMalloc(&zz, (size_t)P * M * 16));
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+  EncodeTiledFn enc = (EncodeTiledFn)fp;
+  CUtensorMap map;
+  cuuint64_t dims[2] = {2, (cuuint64_t)P * M};
+  cuuint64_t strides[1] = {16};
+  cuuint32_t box[2] = {2, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, zz, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  printf("encode: %d\n", (int)r);
+  if (r != CUDA_SUCCESS) return 1;
+  const int upto = argc > 1 ? atoi(argv[1]) : 3;
+  run<0>("st.global.cs.v2.f64 (LSU)", map, zz, P, M);
+  if (upto >= 1) run<1>("scatter4, 128-byte aligned groups", map, zz, P, M);
+  if (upto >= 3) run<3>("scatter4, one lane in four issues", map, zz, P, M);
+  if (upto >= 2) run<2>("scatter4, packed 64-byte groups", map, zz, P, M);
+  return 0;
+}

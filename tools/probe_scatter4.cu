@@ -40,6 +40,23 @@ __global__ void __launch_bounds__(NT) k_scatter(const __grid_constant__ CUtensor
     for (int it = 0; it < IPT; ++it) __stcs(&zz[pbase + pos[it]], make_double2((double)pos[it], (double)p));
     return;
   }
+  if constexpr (MODE == 4) {  // default policy
+#pragma unroll
+    for (int it = 0; it < IPT; ++it) zz[pbase + pos[it]] = make_double2((double)pos[it], (double)p);
+    return;
+  }
+  if constexpr (MODE == 5 || MODE == 6 || MODE == 7) {  // L2 cache hints: evict_last / evict_first / evict_unchanged
+    uint64_t pol;
+    if (MODE == 5) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    if (MODE == 6) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (MODE == 7) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+#pragma unroll
+    for (int it = 0; it < IPT; ++it)
+      asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(&zz[pbase + pos[it]]), "d"((double)pos[it]),
+                   "d"((double)p), "l"(pol)
+                   : "memory");
+    return;
+  }
   __shared__ __align__(128) unsigned char stage[TILE / 4 * 128];
   constexpr uint32_t GSTRIDE = (MODE == 2) ? 64u : 128u;
   // thread t owns groups 2t and 2t+1 (4 pairs each): its own 8 pairs
@@ -95,7 +112,7 @@ void run(const char* name, const CUtensorMap& map, double2* zz, uint32_t P, uint
   k_scatter<MODE><<<dim3(ntiles, P), NT>>>(map, zz, M, ntiles);
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(a));
-  const int reps = 5;
+  const int reps = 20;
   for (int r = 0; r < reps; ++r) k_scatter<MODE><<<dim3(ntiles, P), NT>>>(map, zz, M, ntiles);
   CK(cudaEventRecord(b));
   CK(cudaDeviceSynchronize());
@@ -118,7 +135,7 @@ void run(const char* name, const CUtensorMap& map, double2* zz, uint32_t P, uint
 }
 
 int main(int argc, char** argv) {
-  const uint32_t P = 256, M = 262144;
+  const uint32_t P = argc > 2 ? (uint32_t)atoi(argv[2]) : 256, M = 262144;  // P = 16: the rows (64 MB) stay in L2 between repetitions
   double2* zz;
   CK(cudaMalloc(&zz, (size_t)P * M * 16));
   void* fp = nullptr;
@@ -136,6 +153,10 @@ int main(int argc, char** argv) {
   if (r != CUDA_SUCCESS) return 1;
   const int upto = argc > 1 ? atoi(argv[1]) : 3;
   run<0>("st.global.cs.v2.f64 (LSU)", map, zz, P, M);
+  run<4>("st.global.v2.f64 default", map, zz, P, M);
+  run<5>("st + L2::evict_last", map, zz, P, M);
+  run<6>("st + L2::evict_first", map, zz, P, M);
+  run<7>("st + L2::evict_unchanged", map, zz, P, M);
   if (upto >= 1) run<1>("scatter4, 128-byte aligned groups", map, zz, P, M);
   if (upto >= 3) run<3>("scatter4, one lane in four issues", map, zz, P, M);
   if (upto >= 2) run<2>("scatter4, packed 64-byte groups", map, zz, P, M);

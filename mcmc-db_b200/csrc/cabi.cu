@@ -1189,7 +1189,7 @@ int b200ref_synth_fill_f64(double* x, int64_t p0, int64_t P, int64_t C, int64_t 
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-// [rows][cols] bf16 row-major; box = 64 columns (128 B, one swizzle row) x box_rows rows
+// [rows][cols] bf16 row-major; box = GLM_BK columns (one swizzle row) x box_rows rows
 int make_map_bf16(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(B200REF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -1198,7 +1198,8 @@ int make_map_bf16(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, ui
   cuuint32_t box[2] = {(cuuint32_t)GLM_BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   GLM_BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200REF_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
   return B200REF_OK;
 }
@@ -1218,7 +1219,7 @@ struct GlmLayout {
   size_t bh, bl, xh, xl, yf, af, center, part, hdr, total;
   int Dpad, n_row_tiles, n_draw_tiles, nsplit;
   void compute(int64_t N, int64_t D, int64_t S) {
-    Dpad = (int)((D + GLM_BK - 1) / GLM_BK * GLM_BK);
+    Dpad = (int)((D + GLM_KPAD - 1) / GLM_KPAD * GLM_KPAD);
     n_row_tiles = (int)((N + GLM_BN - 1) / GLM_BN);
     n_draw_tiles = (int)((S + GLM_BM - 1) / GLM_BM);
     // row-tile slices per draw tile: the persistent grid (one CTA per SM) runs ceil(items / SMs) waves of
@@ -1242,7 +1243,7 @@ struct GlmLayout {
     yf = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
     af = o; o += up((size_t)n_row_tiles * GLM_BN * 4);
     center = o; o += up((size_t)Dpad * 8);
-    part = o; o += up((size_t)nsplit * S * 8);
+    part = o; o += up((size_t)nsplit * GLM_PART_SLOTS * S * 8);
     hdr = o; o += up(sizeof(GlmStaged));
     total = o + 1024;
   }
@@ -1314,7 +1315,7 @@ int b200ref_glm_lp_ex_f64(int family, const double* X, const double* y, const do
     want.y = centered ? nullptr : y;  // the staged response of a centred call depends on the draws: never reused
     CUDA_TRY(cudaMemcpyAsync(w + L.hdr, &want, sizeof(want), cudaMemcpyHostToDevice, st));
   }
-  CUDA_TRY(cudaMemsetAsync(part, 0, (size_t)L.nsplit * S * 8, st));
+  CUDA_TRY(cudaMemsetAsync(part, 0, (size_t)L.nsplit * GLM_PART_SLOTS * S * 8, st));
   CUtensorMap mbh, mbl, mxh, mxl;
   int rc;
   if ((rc = make_map_bf16(&mbh, bh, (uint64_t)S, (uint64_t)L.Dpad, GLM_BM))) return rc;
@@ -1344,7 +1345,7 @@ int b200ref_glm_lp_ex_f64(int family, const double* X, const double* y, const do
     case GLM_POISSON_LOG: LAUNCH(K_GLM, st, k_glm_lp<2><<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm)); break;
     default: LAUNCH(K_GLM, st, k_glm_lp<3><<<grid, GLM_NT, GLM_SMEM_BYTES, st>>>(mbh, mbl, mxh, mxl, prm)); break;
   }
-  LAUNCH(K_GLM_PREP, st, k_glm_reduce<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(part, L.nsplit, S,
+  LAUNCH(K_GLM_PREP, st, k_glm_reduce<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(part, L.nsplit * GLM_PART_SLOTS, S,
                                                                                   family == GLM_NORMAL ? sigma : nullptr, N, lp));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(st));

@@ -29,17 +29,37 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200ref {
 
 constexpr int GLM_BM = 128;   // draws per tile   (UMMA M)
 constexpr int GLM_BN = 256;   // data rows per tile (UMMA N)
-constexpr int GLM_BK = 64;    // bf16 elements per k-block: 128 bytes = one swizzle row
-constexpr int GLM_STAGES = 2;
-constexpr int GLM_NT = 384;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
-constexpr int GLM_EPI_WARP0 = 4;
-constexpr int GLM_EPI_THREADS = 256;
+// bf16 elements per k-block = one swizzle row: 64 (128-byte swizzle, 2 stages of 96 KB) or 32 (64-byte swizzle, 4 stages
+// of 48 KB).  Same shared memory, but with 4 stages the producer runs three k-blocks ahead of the MMAs instead of one:
+// a stage's MMAs take ~770 / ~1540 cycles, a TMA round trip for it about as long as the longer of the two.
+#ifndef B200REF_GLM_BK
+#define B200REF_GLM_BK 32
+#endif
+constexpr int GLM_BK = B200REF_GLM_BK;
+static_assert(GLM_BK == 64 || GLM_BK == 32, "one 128-byte or 64-byte swizzle row per k-block");
+constexpr int GLM_KPAD = 64;  // the contraction length is padded to a multiple of this (workspace layout)
+constexpr int GLM_STAGES = (GLM_BK == 64) ? 2 : 4;
+// Epilogue warps: 8 (two per TMEM lane quadrant, 128 accumulator columns each) or 16 (four per quadrant, 64 columns
+// each).  The fused likelihood (two MUFU + ~10 ALU instructions per element) is what the MMAs wait for: with 4 warps
+// per scheduler instead of 2 the MUFU and ALU pipes overlap.
+#ifndef B200REF_GLM_EPI_WARPS
+#define B200REF_GLM_EPI_WARPS 16
+#endif
+constexpr int GLM_EPI_WARPS = B200REF_GLM_EPI_WARPS;
+static_assert(GLM_EPI_WARPS == 8 || GLM_EPI_WARPS == 16, "2 or 4 epilogue warps per TMEM lane quadrant");
+constexpr int GLM_EPI_WARP0 = 4;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
+constexpr int GLM_EPI_THREADS = GLM_EPI_WARPS * 32;
+constexpr int GLM_NT = GLM_EPI_WARP0 * 32 + GLM_EPI_THREADS;
+constexpr int GLM_EPI_COLS = GLM_BN / (GLM_EPI_WARPS / 4);  // accumulator columns per epilogue warp
+constexpr int GLM_PART_SLOTS = GLM_EPI_WARPS / 8;           // partial-sum slots per row slice: exactly two adds each
 constexpr uint32_t GLM_A_BYTES = GLM_BM * GLM_BK * 2;  // 16 KB
 constexpr uint32_t GLM_B_BYTES = GLM_BN * GLM_BK * 2;  // 32 KB
 constexpr uint32_t GLM_STAGE_BYTES = 2 * GLM_A_BYTES + 2 * GLM_B_BYTES;  // 96 KB
@@ -60,7 +80,7 @@ struct GlmParams {
   int nsplit;          // row-tile slices per draw tile
   const float* yf;     // [n_row_tiles * 256] y as float, padded with 0
   const float* af;     // [n_row_tiles * 256] binomial trials as float (binomial_logit), else unused
-  double* lp_part;     // [nsplit][S], zero-initialised
+  double* lp_part;     // [nsplit * GLM_PART_SLOTS][S], zero-initialised
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -102,13 +122,14 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 
 // K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart):
 // start address >> 4 | LBO 1 | SBO 64 (1024 B >> 4) | version 1 (Blackwell) | layout SWIZZLE_128B (2)
+// (64-byte swizzle, GLM_BK = 32: rows of 64 B, 8-row groups 512 B apart: SBO 32, layout SWIZZLE_64B (4))
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)64 << 32;
+  d |= (uint64_t)(GLM_BK == 64 ? 64 : 32) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(GLM_BK == 64 ? 2 : 4) << 61;
   return d;
 }
 // kind::f16: D fp32 (bits 4-5 = 1), A bf16 (bits 7-9 = 1), B bf16 (bits 10-12 = 1), both K-major,
@@ -183,11 +204,11 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
   float* ys = (float*)(smem + (size_t)GLM_STAGES * GLM_STAGE_BYTES);  // [2][256] y, then [2][256] trials
   float* as = ys + 2 * GLM_BN;
   uint64_t* bars = (uint64_t*)(ys + 4 * GLM_BN);
-  uint64_t* full = bars;            // [2]  TMA -> MMA
-  uint64_t* empty = bars + 2;       // [2]  MMA -> TMA
-  uint64_t* tfull = bars + 4;       // [2]  MMA -> epilogue
-  uint64_t* tempty = bars + 6;      // [2]  epilogue -> MMA
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  uint64_t* full = bars;                         // [GLM_STAGES]  TMA -> MMA
+  uint64_t* empty = bars + GLM_STAGES;           // [GLM_STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * GLM_STAGES;       // [2]  MMA -> epilogue
+  uint64_t* tempty = bars + 2 * GLM_STAGES + 2;  // [2]  epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * GLM_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = prm.Dpad / GLM_BK;
@@ -266,10 +287,10 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
     }
   } else if (warp >= GLM_EPI_WARP0) {
     // ================= epilogue: eta -> y*eta - softplus(eta), summed over data rows =================
-    const int ew = warp - GLM_EPI_WARP0;       // 0..7
+    const int ew = warp - GLM_EPI_WARP0;       // 0 .. GLM_EPI_WARPS-1
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int chalf = ew >> 2;                 // which 128 columns
-    const int et = threadIdx.x - GLM_EPI_WARP0 * 32;  // 0..255
+    const int cpart = ew >> 2;                 // which GLM_EPI_COLS columns
+    const int et = threadIdx.x - GLM_EPI_WARP0 * 32;  // 0 .. GLM_EPI_THREADS-1
     const int row = quad * 32 + lane;          // draw within the tile
     int abuf = 0;
     uint32_t aphase = 0;
@@ -279,9 +300,11 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
       const int t0 = h * tiles_per_split, t1 = min(t0 + tiles_per_split, prm.n_row_tiles);
       double acc = 0.0;
       for (int rt = t0; rt < t1; ++rt) {
-        // stage y for this tile's 256 data rows (one element per epilogue thread)
-        ys[abuf * GLM_BN + et] = prm.yf[(size_t)rt * GLM_BN + et];
-        if (FAM == GLM_BINOMIAL_LOGIT) as[abuf * GLM_BN + et] = prm.af[(size_t)rt * GLM_BN + et];
+        // stage y for this tile's 256 data rows (one element per thread of the first 8 epilogue warps)
+        if (et < GLM_BN) {
+          ys[abuf * GLM_BN + et] = prm.yf[(size_t)rt * GLM_BN + et];
+          if (FAM == GLM_BINOMIAL_LOGIT) as[abuf * GLM_BN + et] = prm.af[(size_t)rt * GLM_BN + et];
+        }
         mbar_wait(&tfull[abuf], aphase);
         tc_fence_after();
         asm volatile("bar.sync 1, %0;" ::"n"(GLM_EPI_THREADS) : "memory");
@@ -290,51 +313,58 @@ k_glm_lp(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUt
         // 1 KB round-up of the dynamic shared-memory base goes through an integer, after which the compiler only
         // knows a generic pointer and emits LD.E instead of LDS)
         const uint32_t yt4 = smem_u32(ys + abuf * GLM_BN), at4 = smem_u32(as + abuf * GLM_BN);
+        // MASK: only the last row tile of the design has rows that do not exist (their terms are dropped)
+        auto tile_terms = [&](auto mask_tag) {
+          constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int col0 = chalf * 128 + cc * 32;
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(abuf * GLM_BN + col0), v);
-          float part = 0.0f;
+          for (int cc = 0; cc < GLM_EPI_COLS / 32; ++cc) {
+            const int col0 = cpart * GLM_EPI_COLS + cc * 32;
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(abuf * GLM_BN + col0), v);
+            float part = 0.0f;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 y4 = lds128(yt4 + (uint32_t)(col0 + 4 * j4) * 4u);
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (FAM == GLM_BINOMIAL_LOGIT) a4 = lds128(at4 + (uint32_t)(col0 + 4 * j4) * 4u);
-            const float yy[4] = {y4.x, y4.y, y4.z, y4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 y4 = lds128(yt4 + (uint32_t)(col0 + 4 * j4) * 4u);
+              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (FAM == GLM_BINOMIAL_LOGIT) a4 = lds128(at4 + (uint32_t)(col0 + 4 * j4) * 4u);
+              const float yy[4] = {y4.x, y4.y, y4.z, y4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int j = 4 * j4 + q;
-              const float eta = __uint_as_float(v[j]);
-              float term;
-              if (FAM == GLM_BERNOULLI_LOGIT || FAM == GLM_BINOMIAL_LOGIT) {
-                const float a = fabsf(eta);
-                float e, l;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * LOG2E));
-                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-                const float sp = fmaxf(eta, 0.0f) + l * LN2;  // softplus
-                term = yy[q] * eta - ((FAM == GLM_BINOMIAL_LOGIT) ? aa[q] * sp : sp);
-              } else if (FAM == GLM_POISSON_LOG) {
-                float e;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(eta * LOG2E));
-                term = yy[q] * eta - e;
-              } else {
-                const float r = yy[q] - eta;
-                term = -r * r;
+              for (int q = 0; q < 4; ++q) {
+                const int j = 4 * j4 + q;
+                const float eta = __uint_as_float(v[j]);
+                float term;
+                if (FAM == GLM_BERNOULLI_LOGIT || FAM == GLM_BINOMIAL_LOGIT) {
+                  const float a = fabsf(eta);
+                  float e, l;
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * LOG2E));
+                  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+                  const float sp = fmaxf(eta, 0.0f) + l * LN2;  // softplus
+                  term = yy[q] * eta - ((FAM == GLM_BINOMIAL_LOGIT) ? aa[q] * sp : sp);
+                } else if (FAM == GLM_POISSON_LOG) {
+                  float e;
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(eta * LOG2E));
+                  term = yy[q] * eta - e;
+                } else {
+                  const float r = yy[q] - eta;
+                  term = -r * r;
+                }
+                if (MASK && col0 + j >= nvalid) term = 0.0f;
+                part += term;
               }
-              if (col0 + j >= nvalid) term = 0.0f;
-              part += term;
             }
+            acc += (double)part;
           }
-          acc += (double)part;
-        }
+        };
+        if (nvalid >= GLM_BN) tile_terms(std::false_type{});
+        else tile_terms(std::true_type{});
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[abuf]);
         if (++abuf == 2) { abuf = 0; aphase ^= 1; }
       }
       const int64_t s = (int64_t)dt * GLM_BM + row;
-      if (s < prm.S) atomicAdd(&prm.lp_part[(size_t)h * prm.S + s], acc);  // exactly two adds: order-free
+      // two warps share a slot: exactly two adds, order-free
+      if (s < prm.S) atomicAdd(&prm.lp_part[((size_t)h * GLM_PART_SLOTS + (cpart >> 1)) * prm.S + s], acc);
     }
   }
   tc_fence_before();

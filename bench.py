@@ -229,6 +229,10 @@ def diag_measure(args, wname: str, rank: int, world: int, local: int, full: bool
         return line
 
     # ---- end to end from HOST buffers through the public call (H2D + D2H inside the timed region) ----
+    # the pinned buffers are allocated after the process has been bound to its GPU's NUMA node (a no-op on a box
+    # that exposes a single node); the affinity is restored for the CPU baseline's process pool below
+    affinity0 = os.sched_getaffinity(0)
+    host_topology = sharding.bind_host_to_gpu(local)
     cand_h = cand.cpu().pin_memory()
     ref_h = ref.cpu().pin_memory()
     sum_h = torch.empty((P, len(batch.SUMMARY_COLUMNS)), dtype=torch.float64).pin_memory()
@@ -256,9 +260,11 @@ def diag_measure(args, wname: str, rank: int, world: int, local: int, full: bool
            "steps": e2e_steps, "h2d_gbs_aggregate": round(h2d * e2e_steps / e2e_sec / 1e9, 1),
            "limiter": "host->device copy: the pass is PCIe-bound end to end (h2d_gbs_aggregate is the whole box's "
                       "pinned-memory H2D rate over all ranks; the device-resident `value` is what the kernels sustain)",
+           "host_topology": host_topology,
            "call": "mcmc_ref_b200.batch.full_pass_host -> b200ref_full_pass_host_f64 (pinned host buffers)"}
     same_bits = bool(np.array_equal(s_host.numpy(), summary.cpu().numpy(), equal_nan=True))
     del cand_h, ref_h
+    os.sched_setaffinity(0, affinity0)
 
     # ---- CPU baseline + parity gate on a bounded sample (rank 0, N = 1 only) ----
     cpu_baseline = None

@@ -10,8 +10,45 @@ synchronisation inside the step.
 
 from __future__ import annotations
 
+import os
+from pathlib import Path
+
 import torch
 import torch.distributed as dist
+
+
+def _cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host buffers
+    (first touch then places them on that node), so that several ranks of one box do not pull their host -> device
+    copies across the socket interconnect.  Reads sysfs; a box that exposes one node (or none for the GPU, as VMs do)
+    is left alone.  Returns what it found and did -- bench.py puts it next to the end-to-end number."""
+    info: dict = {"numa_nodes": None, "gpu_numa_node": None, "cpus_bound": None}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        addr = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        nodes = sorted(Path("/sys/devices/system/node").glob("node[0-9]*"))
+        info["numa_nodes"] = len(nodes)
+        node = int(Path(f"/sys/bus/pci/devices/{addr}/numa_node").read_text())
+        info["gpu_numa_node"] = node
+        if node >= 0 and len(nodes) > 1:
+            cpus = _cpulist(Path(f"/sys/devices/system/node/node{node}/cpulist").read_text())
+            allowed = os.sched_getaffinity(0) & cpus
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["cpus_bound"] = len(allowed)
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError) as exc:  # no sysfs, no such device: nothing to bind
+        info["error"] = type(exc).__name__
+    return info
 
 
 def shard_bounds(n_params: int, world: int, rank: int) -> tuple[int, int]:

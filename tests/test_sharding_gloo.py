@@ -79,3 +79,21 @@ def test_gather_and_verdict_world2(n_params):
         assert ok_order and ok_auto and ok_lp, rank
         assert v_all is True and v_one is False
         assert v_col_all is True and v_col_one is False
+
+
+def test_cpulist_and_numa_binding_without_a_gpu():
+    """sysfs cpulist syntax; without a CUDA device (this container) the binding reports why it did nothing and
+    leaves the affinity alone."""
+    import os
+
+    from mcmc_ref_b200 import sharding
+
+    assert sharding._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding._cpulist("5") == {5} and sharding._cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = sharding.bind_host_to_gpu(0)
+    assert set(info) >= {"numa_nodes", "gpu_numa_node", "cpus_bound"}
+    import torch
+
+    if not torch.cuda.is_available():
+        assert info["cpus_bound"] is None and os.sched_getaffinity(0) == before

@@ -167,6 +167,10 @@ inline int fold_bin_shift(int64_t M) {
 #ifndef B200REF_MOMENTS_TILE
 #define B200REF_MOMENTS_TILE 1
 #endif
+// Round 0 covers 48 instead of 16 lags for the parameters k_predict_sticky marks (tile variant only)
+#ifndef B200REF_STICKY_ROUND0
+#define B200REF_STICKY_ROUND0 1
+#endif
 inline bool use_slabs(int64_t M) { return B200REF_SINGLE_PASS != 0 && choose_sub(M) == 1; }
 // records of one parameter's slab region: 3 x the mean per bucket + 64 (k_sample), + room for pure buckets
 inline size_t slab_records(int64_t M) { return use_slabs(M) ? (size_t)5 * (size_t)M + 32768 : (size_t)M; }
@@ -175,7 +179,7 @@ inline size_t slab_records(int64_t M) { return use_slabs(M) ? (size_t)5 * (size_
 struct Layout {
   size_t ztab, zodd, flag, header;  // shared part
   size_t pkey, skey, pidx, sidx, kcode, zz, rzf, bcur, fn, cnt, boff, cur, spart, fallback, nfb, plist, nbigb, biglist, hist, sel, sum, mean, sd, med, m0, apos,
-      crhat, cess, clag, cpart, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cgpend, cgprev, cwl0, cwl1, cnwl, cgbar, per_batch;
+      crhat, cess, clag, cpart, csticky, cpartr, cmean, csum, chead, ctail, cvarhat, crhosum, cgpend, cgprev, cwl0, cwl1, cnwl, cgbar, per_batch;
   uint32_t ntiles, nchunks;
   void compute(int64_t PB, int64_t M, bool diag, int64_t C = 1, int64_t N = 1) {
     ntiles = (uint32_t)((M + RANK_TILE - 1) / RANK_TILE);
@@ -224,6 +228,7 @@ struct Layout {
       const ChainGeom g = chain_geom(C, N);
       const size_t units = (size_t)C * g.nunits;
       cpart = b; b += up((size_t)PB * units * 2 * MO_VALS * 8);
+      csticky = b; b += up((size_t)PB);
       cpartr = b; b += up((size_t)2 * PB * units * LAGR * 8);
       cmean = b; b += up((size_t)2 * PB * C * 8);
       csum = b; b += up((size_t)2 * PB * C * 8);
@@ -413,6 +418,7 @@ int launch_chain_stats(const double2* zz, int PB, int64_t C, int64_t N, char* wb
   const ChainGeom g = chain_geom(C, N);
   cs.part = (double*)(wb + L.cpart);
   cs.partr = (double*)(wb + L.cpartr);
+  cs.sticky = (uint8_t*)(wb + L.csticky);
   cs.cmean = (double*)(wb + L.cmean);
   cs.csum = (double*)(wb + L.csum);
   cs.head = (double*)(wb + L.chead);
@@ -431,7 +437,13 @@ int launch_chain_stats(const double2* zz, int PB, int64_t C, int64_t N, char* wb
     const uint32_t upc = std::max<uint32_t>(1u, MO_CTA_TILES / g.tpu);
     const unsigned gx = (unsigned)((C * g.nunits + upc - 1) / upc);
     if (B200REF_MOMENTS_TILE != 0 && (N % 8) == 0 && ((uintptr_t)zz % 128) == 0) {
-      // tile variant: 2-D TMA into swizzled landing buffers, both kinds per thread (no de-interleave pass)
+      // tile variant: 2-D TMA into swizzled landing buffers, both kinds per thread (no de-interleave pass); for the
+      // parameters whose first chain looks sticky it also covers lags 17 .. 48
+      if (B200REF_STICKY_ROUND0) {
+        LAUNCH(K_CHAIN, st, k_predict_sticky<<<(PB + 3) / 4, 128, 0, st>>>(zz, g, PB, cs.sticky));
+      } else {
+        CUDA_TRY(cudaMemsetAsync(cs.sticky, 0, (size_t)PB, st));
+      }
       CUtensorMap map;
       const int rc = make_map_pairs(&map, zz, (uint64_t)PB * (uint64_t)C * (uint64_t)(N / 8));
       if (rc) return rc;
@@ -439,8 +451,9 @@ int launch_chain_stats(const double2* zz, int PB, int64_t C, int64_t N, char* wb
       const uint32_t upw = std::max<uint32_t>(1u, 32u / (g.tpu * (MO_SUB / 8 / M2_ROWS)));
       const uint32_t upc_t = M2_NW * upw;
       const unsigned gxt = (unsigned)((C * g.nunits + upc_t - 1) / upc_t);
-      LAUNCH(K_CHAIN, st, k_moments0t<<<dim3(gxt, PB), M2_NT, M2_SMEM, st>>>(map, g, upc_t, cs.part));
+      LAUNCH(K_CHAIN, st, k_moments0t<<<dim3(gxt, PB), M2_NT, M2_SMEM, st>>>(map, g, upc_t, cs.part, cs.sticky));
     } else {
+      CUDA_TRY(cudaMemsetAsync(cs.sticky, 0, (size_t)PB, st));
       LAUNCH(K_CHAIN, st, k_moments0<<<dim3(gx, PB), MO_CTA, sizeof(Mo0Smem), st>>>(zz, g, upc, cs.part));
     }
   }

@@ -22,6 +22,8 @@
 // Because all chains of a parameter have the same length n, sum_c cov_c / (n - t) is
 // accumulated as (sum_c S_c) / (n - t).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200ref {
@@ -40,7 +42,9 @@ constexpr int MO_UNIT_TILES = B200REF_MO_UNIT_TILES;  // a unit (one CTA) covers
 #define B200REF_MO_CTA_TILES 12
 #endif
 constexpr int MO_CTA_TILES = B200REF_MO_CTA_TILES;  // sub-tiles one round-0 CTA streams (several units)
-constexpr int MO_VALS = LAGB + 10;       // per (unit, kind) in round 0: 16 lag sums + 2 x {sum, sq, first, differs, present}
+constexpr int MO_VALS0 = LAGB + 10;      // per (unit, kind) in round 0: 16 lag sums + 2 x {sum, sq, first, differs, present}
+constexpr int LAG0X = 2 * LAGB;          // + lags 17 .. 48 for the parameters k_predict_sticky marks (tile variant only)
+constexpr int MO_VALS = MO_VALS0 + LAG0X;  // stride of a (unit, kind) record: [0,16) lags 1..16, [16,26) moments, [26,58) lags 17..48
 constexpr int DEC_NT = 64;
 
 // Chains are cut into units of whole 2048-draw sub-tiles, independent of the split point: the lag
@@ -96,6 +100,7 @@ __device__ __forceinline__ double warp_reduce_16(double (&v)[16]) {
 
 struct ChainState {
   double* part;      // [PB][C*nunits][2][MO_VALS] round-0 partial sums
+  uint8_t* sticky;   // [PB] 1: round 0 also covers lags 17 .. 48 of this parameter (k_predict_sticky)
   double* partr;     // [nwork][C*nunits][LAGR]   later rounds
   double* cmean;     // [2*PB][C]  unsplit chain means
   double* csum;      // [2*PB][C]  chain totals
@@ -140,7 +145,7 @@ __device__ __forceinline__ void stage_pairs(double2* raw, const double2* src, ui
 struct Mo0Smem {
   double2 raw[MO_RAW0];
   double y[2][2][MO_PAD0];  // [buffer][kind]
-  double red[2][MO_NT / 32][MO_VALS];
+  double red[2][MO_NT / 32][MO_VALS0];
   uint64_t bar;
 };
 
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restric
       r[21] = s2; r[22] = q2; r[23] = f2; r[24] = w2 ? 1.0 : 0.0; r[25] = has2 ? 1.0 : 0.0;
     }
     __syncthreads();
-    if (ct < MO_VALS) {
+    if (ct < MO_VALS0) {
       double v = S.red[kind][0][ct];
       const bool copy = (ct == 18 || ct == 20 || ct == 23 || ct == 25);  // first values / presence: not summed
       if (!copy) {
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_moments0(const double2* __restric
 constexpr int M2_NT = 128;                       // threads per CTA (4 independent warps)
 constexpr int M2_NW = M2_NT / 32;
 constexpr int M2_ROWS = 32;                      // rows per tile = lanes
-constexpr int M2_BOX = M2_ROWS + 2;              // + 2 halo rows: the 16 draws after the tile's last one
+constexpr int M2_BOX = M2_ROWS + 6;              // + halo rows: the 16 draws after the tile's last one (lags 1 .. 16), 48 for lags up to 48
 constexpr int M2_TILE_BYTES = M2_BOX * 128;
 constexpr int M2_STAGE = ((M2_TILE_BYTES + 1023) / 1024) * 1024;  // landing buffers are 1024-byte aligned (swizzle atom)
 #ifndef B200REF_M2_NST
@@ -337,8 +342,43 @@ __device__ __forceinline__ double warp_reduce_8(double (&v)[8]) {
   return t + __shfl_xor_sync(FULL, t, 16);
 }
 
+// One warp per parameter looks at the first draws of its first chain: is the lag-8 autocorrelation of either score
+// far above its sampling error?  Then most of this parameter's chains will still be correlated after the 16 lags of
+// round 0, and round 0 covers 48 lags for it in the same (tile) kernel instead of leaving lags 17 .. 48 to the
+// slower later rounds.  Only the COST depends on the guess: lag sums are formed in the same way wherever they are
+// computed, and a parameter that is guessed wrong just takes the other route.
+constexpr uint32_t STICKY_DRAWS = 1024;
+__global__ void __launch_bounds__(128) k_predict_sticky(const double2* __restrict__ zz, ChainGeom g, int PB, uint8_t* __restrict__ sticky) {
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= PB) return;
+  const double2* z = zz + (size_t)p * g.C * g.N;  // chain 0
+  const uint32_t L = min(g.N, STICKY_DRAWS);
+  uint8_t out = 0;
+  if (g.N >= 128u) {
+    double s[2] = {0.0, 0.0}, q[2] = {0.0, 0.0}, c8[2] = {0.0, 0.0};
+    for (uint32_t i = lane; i < L; i += 32) {
+      const double2 a = z[i];
+      s[0] += a.x; q[0] = fma(a.x, a.x, q[0]);
+      s[1] += a.y; q[1] = fma(a.y, a.y, q[1]);
+      if (i + 8 < L) {
+        const double2 b = z[i + 8];
+        c8[0] = fma(a.x, b.x, c8[0]);
+        c8[1] = fma(a.y, b.y, c8[1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double ss = warp_sum(s[k]), qq = warp_sum(q[k]), cc = warp_sum(c8[k]);
+      const double m = ss / (double)L, var = qq / (double)L - m * m;
+      const double rho8 = (var > 0.0) ? (cc / (double)(L - 8) - m * m) / var : 0.0;
+      if (rho8 > 0.15) out = 1;
+    }
+  }
+  if (lane == 0) sticky[p] = out;
+}
+
 __global__ void __launch_bounds__(M2_NT, B200REF_M2_OCC) k_moments0t(const __grid_constant__ CUtensorMap map, ChainGeom g, uint32_t upc,
-                                                                     double* part) {
+                                                                     double* part, const uint8_t* __restrict__ sticky) {
   extern __shared__ __align__(128) unsigned char mo_smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(mo_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int p = blockIdx.y;
@@ -350,6 +390,9 @@ __global__ void __launch_bounds__(M2_NT, B200REF_M2_OCC) k_moments0t(const __gri
   const uint32_t unit0 = blockIdx.x * upc + wp, unit1 = min(blockIdx.x * upc + upc, nu);  // this warp: unit0, unit0 + 4, ...
   const uint32_t Rc = g.N >> 3;                          // rows per chain
   const uint32_t prow0 = (uint32_t)p * g.C * Rc;         // first row of this parameter
+  // passes over a unit: lags 1 .. 16 (+ the moments); for a parameter marked sticky also lags 17 .. 32 and 33 .. 48
+  // (the unit's tiles come again, from L2: the same loop with the partner rows 2 and 4 rows further on)
+  const uint32_t nb = sticky[p] ? 3u : 1u;
   if (lane == 0) {
     for (int s = 0; s < M2_NST; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
@@ -364,7 +407,7 @@ __global__ void __launch_bounds__(M2_NT, B200REF_M2_OCC) k_moments0t(const __gri
     rb = b >> 3;
   };
   // producer cursor (lane 0): the next tile to request
-  uint32_t iu = unit0, it_ = 0, issued = 0;
+  uint32_t iu = unit0, ib = 0, it_ = 0, issued = 0;
   auto issue_next = [&]() {  // lane 0 only
     while (iu < unit1) {
       uint32_t c, ra, rb;
@@ -379,122 +422,160 @@ __global__ void __launch_bounds__(M2_NT, B200REF_M2_OCC) k_moments0t(const __gri
         ++issued;
         return;
       }
-      iu += M2_NW;
       it_ = 0;
+      if (++ib == nb) { ib = 0; iu += M2_NW; }
     }
   };
   if (lane == 0)
     for (int s = 0; s < M2_NST; ++s) issue_next();
   const uint32_t half = g.half;
   uint32_t seq = 0;  // tiles consumed so far by this warp
+  // 16 lag products of this lane's row (8 draws, both kinds) against the rows o, o + 1, o + 2 after it: lags
+  // 8 o + 1 .. 8 o + 16.  FIRST (o = 0): the first partner row is the lane's own row, already in registers.
+  auto lag_block = [&](auto first_tag, uint32_t tile, uint32_t rc, uint32_t o, const double2 (&v)[8], double (&accb)[LAGB],
+                       double (&accf)[LAGB]) {
+    constexpr bool FIRST = decltype(first_tag)::value;
+    if (FIRST || rc + o < Rc) {
+#pragma unroll
+      for (int j = 1; j < 8; ++j) {
+        const double2 w = FIRST ? v[j] : m2_pair(tile, lane + o, j);
+#pragma unroll
+        for (int s = 0; s < j; ++s) {
+          accb[j - s - 1] = fma(v[s].x, w.x, accb[j - s - 1]);
+          accf[j - s - 1] = fma(v[s].y, w.y, accf[j - s - 1]);
+        }
+      }
+    }
+    if (rc + o + 1 < Rc) {  // next row (same chain)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double2 w = m2_pair(tile, lane + o + 1, j);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          accb[8 + j - s - 1] = fma(v[s].x, w.x, accb[8 + j - s - 1]);
+          accf[8 + j - s - 1] = fma(v[s].y, w.y, accf[8 + j - s - 1]);
+        }
+      }
+    }
+    if (rc + o + 2 < Rc) {  // the row after
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double2 w = m2_pair(tile, lane + o + 2, j);
+#pragma unroll
+        for (int s = j; s < 8; ++s) {
+          accb[16 + j - s - 1] = fma(v[s].x, w.x, accb[16 + j - s - 1]);
+          accf[16 + j - s - 1] = fma(v[s].y, w.y, accf[16 + j - s - 1]);
+        }
+      }
+    }
+  };
   for (uint32_t unit = unit0; unit < unit1; unit += M2_NW) {
     uint32_t c, ra, rb;
     unit_rows(unit, c, ra, rb);
     const uint32_t a = ra << 3, b = rb << 3;
-    const bool has1 = a < half, has2 = b > half && max(a, half) < 2 * half;
-    const uint32_t pos2 = max(a, half);
-    double accb[LAGB], accf[LAGB];
-#pragma unroll
-    for (int l = 0; l < LAGB; ++l) { accb[l] = 0.0; accf[l] = 0.0; }
-    double hs[8];  // s1b q1b s2b q2b s1f q1f s2f q2f
-#pragma unroll
-    for (int l = 0; l < 8; ++l) hs[l] = 0.0;
-    double2 f1 = make_double2(0.0, 0.0), f2 = make_double2(0.0, 0.0);
-    bool d1b = false, d2b = false, d1f = false, d2f = false;
     const uint32_t ntile = (rb - ra + M2_ROWS - 1) / M2_ROWS;
-    for (uint32_t ti = 0; ti < ntile; ++ti, ++seq) {
-      const uint32_t st = seq % M2_NST;
-      const uint32_t tile = wbase_s + st * (uint32_t)M2_STAGE;
-      mbar_wait(&full[st], (seq / M2_NST) & 1u);
-      const uint32_t row0 = ra + ti * M2_ROWS;  // chain row of the tile's first row
-      if (ti == 0 && has1) f1 = m2_pair(tile, 0, 0);
-      if (has2 && (pos2 >> 3) >= row0 && (pos2 >> 3) < row0 + M2_ROWS) f2 = m2_pair(tile, (pos2 >> 3) - row0, pos2 & 7u);
-      const uint32_t rc = row0 + lane;          // this lane's row of the chain
-      if (rc < rb) {
-        double2 v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = m2_pair(tile, lane, k);
-        // partners inside the row: lags 1 .. 7
-#pragma unroll
-        for (int j = 1; j < 8; ++j) {
-#pragma unroll
-          for (int s = 0; s < j; ++s) {
-            accb[j - s - 1] = fma(v[s].x, v[j].x, accb[j - s - 1]);
-            accf[j - s - 1] = fma(v[s].y, v[j].y, accf[j - s - 1]);
-          }
-        }
-        if (rc + 1 < Rc) {  // next row (same chain): lags 1 .. 15
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const double2 w = m2_pair(tile, lane + 1, j);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-              accb[8 + j - s - 1] = fma(v[s].x, w.x, accb[8 + j - s - 1]);
-              accf[8 + j - s - 1] = fma(v[s].y, w.y, accf[8 + j - s - 1]);
-            }
-          }
-        }
-        if (rc + 2 < Rc) {  // the row after: lags 9 .. 16
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const double2 w = m2_pair(tile, lane + 2, j);
-#pragma unroll
-            for (int s = j; s < 8; ++s) {
-              accb[16 + j - s - 1] = fma(v[s].x, w.x, accb[16 + j - s - 1]);
-              accf[16 + j - s - 1] = fma(v[s].y, w.y, accf[16 + j - s - 1]);
-            }
-          }
-        }
-        // per-half sums, sums of squares and "some draw differs from the half's first one" (bit patterns: scores are
-        // table entries, equal values are equal bits)
-        const uint32_t g0 = rc << 3;
-        const bool in1 = g0 + 8 <= half, in2 = g0 >= half && g0 + 8 <= 2 * half;
-        if (in1 || in2) {
-          const long long rb_ = __double_as_longlong(in1 ? f1.x : f2.x), rf_ = __double_as_longlong(in1 ? f1.y : f2.y);
-          double lsb = 0.0, lqb = 0.0, lsf = 0.0, lqf = 0.0;
-          bool ldb = false, ldf = false;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            lsb += v[s].x; lqb = fma(v[s].x, v[s].x, lqb); ldb |= (__double_as_longlong(v[s].x) != rb_);
-            lsf += v[s].y; lqf = fma(v[s].y, v[s].y, lqf); ldf |= (__double_as_longlong(v[s].y) != rf_);
-          }
-          if (in1) { hs[0] += lsb; hs[1] += lqb; d1b |= ldb; hs[4] += lsf; hs[5] += lqf; d1f |= ldf; }
-          else     { hs[2] += lsb; hs[3] += lqb; d2b |= ldb; hs[6] += lsf; hs[7] += lqf; d2f |= ldf; }
-        } else {
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const uint32_t gi = g0 + s;
-            if (gi < half) {
-              hs[0] += v[s].x; hs[1] = fma(v[s].x, v[s].x, hs[1]); d1b |= (v[s].x != f1.x);
-              hs[4] += v[s].y; hs[5] = fma(v[s].y, v[s].y, hs[5]); d1f |= (v[s].y != f1.y);
-            } else if (gi < 2 * half) {
-              hs[2] += v[s].x; hs[3] = fma(v[s].x, v[s].x, hs[3]); d2b |= (v[s].x != f2.x);
-              hs[6] += v[s].y; hs[7] = fma(v[s].y, v[s].y, hs[7]); d2f |= (v[s].y != f2.y);
-            }
-          }
-        }
-      }
-      __syncwarp();  // every lane has read the landing buffer: it can take the next copy
-      if (lane == 0) issue_next();
-    }
-    // unit totals (fixed order): halving reduces inside the warp, written straight to the unit's partial sums
-    const double totb = warp_reduce_16(accb);
-    const double totf = warp_reduce_16(accf);
-    const double toth = warp_reduce_8(hs);
-    const bool w1b = __any_sync(FULL, d1b), w2b = __any_sync(FULL, d2b), w1f = __any_sync(FULL, d1f), w2f = __any_sync(FULL, d2f);
     double* pb = part + (((size_t)p * nu + unit) * 2 + 0) * MO_VALS;
     double* pf = pb + MO_VALS;
-    if (lane < LAGB) { pb[lane] = totb; pf[lane] = totf; }
-    // lane l (< 8) holds hs[l]: s1b q1b s2b q2b | s1f q1f s2f q2f
-    if (lane < 4) pb[16 + (lane >> 1) * 5 + (lane & 1)] = toth;
-    else if (lane < 8) pf[16 + ((lane - 4) >> 1) * 5 + (lane & 1)] = toth;
-    if (lane == 8) {
-      pb[18] = f1.x; pb[19] = w1b ? 1.0 : 0.0; pb[20] = has1 ? 1.0 : 0.0;
-      pb[23] = f2.x; pb[24] = w2b ? 1.0 : 0.0; pb[25] = has2 ? 1.0 : 0.0;
+    // ---- pass 0: lags 1 .. 16 and the moments
+    {
+      const bool has1 = a < half, has2 = b > half && max(a, half) < 2 * half;
+      const uint32_t pos2 = max(a, half);
+      double accb[LAGB], accf[LAGB];
+#pragma unroll
+      for (int l = 0; l < LAGB; ++l) { accb[l] = 0.0; accf[l] = 0.0; }
+      double hs[8];  // s1b q1b s2b q2b s1f q1f s2f q2f
+#pragma unroll
+      for (int l = 0; l < 8; ++l) hs[l] = 0.0;
+      double2 f1 = make_double2(0.0, 0.0), f2 = make_double2(0.0, 0.0);
+      bool d1b = false, d2b = false, d1f = false, d2f = false;
+      for (uint32_t ti = 0; ti < ntile; ++ti, ++seq) {
+        const uint32_t st = seq % M2_NST;
+        const uint32_t tile = wbase_s + st * (uint32_t)M2_STAGE;
+        mbar_wait(&full[st], (seq / M2_NST) & 1u);
+        const uint32_t row0 = ra + ti * M2_ROWS;  // chain row of the tile's first row
+        if (ti == 0 && has1) f1 = m2_pair(tile, 0, 0);
+        if (has2 && (pos2 >> 3) >= row0 && (pos2 >> 3) < row0 + M2_ROWS) f2 = m2_pair(tile, (pos2 >> 3) - row0, pos2 & 7u);
+        const uint32_t rc = row0 + lane;          // this lane's row of the chain
+        if (rc < rb) {
+          double2 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = m2_pair(tile, lane, k);
+          lag_block(std::true_type{}, tile, rc, 0u, v, accb, accf);
+          // per-half sums, sums of squares and "some draw differs from the half's first one" (bit patterns: scores are
+          // table entries, equal values are equal bits)
+          const uint32_t g0 = rc << 3;
+          const bool in1 = g0 + 8 <= half, in2 = g0 >= half && g0 + 8 <= 2 * half;
+          if (in1 || in2) {
+            const long long rb_ = __double_as_longlong(in1 ? f1.x : f2.x), rf_ = __double_as_longlong(in1 ? f1.y : f2.y);
+            double lsb = 0.0, lqb = 0.0, lsf = 0.0, lqf = 0.0;
+            bool ldb = false, ldf = false;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              lsb += v[s].x; lqb = fma(v[s].x, v[s].x, lqb); ldb |= (__double_as_longlong(v[s].x) != rb_);
+              lsf += v[s].y; lqf = fma(v[s].y, v[s].y, lqf); ldf |= (__double_as_longlong(v[s].y) != rf_);
+            }
+            if (in1) { hs[0] += lsb; hs[1] += lqb; d1b |= ldb; hs[4] += lsf; hs[5] += lqf; d1f |= ldf; }
+            else     { hs[2] += lsb; hs[3] += lqb; d2b |= ldb; hs[6] += lsf; hs[7] += lqf; d2f |= ldf; }
+          } else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              const uint32_t gi = g0 + s;
+              if (gi < half) {
+                hs[0] += v[s].x; hs[1] = fma(v[s].x, v[s].x, hs[1]); d1b |= (v[s].x != f1.x);
+                hs[4] += v[s].y; hs[5] = fma(v[s].y, v[s].y, hs[5]); d1f |= (v[s].y != f1.y);
+              } else if (gi < 2 * half) {
+                hs[2] += v[s].x; hs[3] = fma(v[s].x, v[s].x, hs[3]); d2b |= (v[s].x != f2.x);
+                hs[6] += v[s].y; hs[7] = fma(v[s].y, v[s].y, hs[7]); d2f |= (v[s].y != f2.y);
+              }
+            }
+          }
+        }
+        __syncwarp();  // every lane has read the landing buffer: it can take the next copy
+        if (lane == 0) issue_next();
+      }
+      // unit totals (fixed order): halving reduces inside the warp, written straight to the unit's partial sums
+      const double totb = warp_reduce_16(accb);
+      const double totf = warp_reduce_16(accf);
+      const double toth = warp_reduce_8(hs);
+      const bool w1b = __any_sync(FULL, d1b), w2b = __any_sync(FULL, d2b), w1f = __any_sync(FULL, d1f), w2f = __any_sync(FULL, d2f);
+      if (lane < LAGB) { pb[lane] = totb; pf[lane] = totf; }
+      // lane l (< 8) holds hs[l]: s1b q1b s2b q2b | s1f q1f s2f q2f
+      if (lane < 4) pb[16 + (lane >> 1) * 5 + (lane & 1)] = toth;
+      else if (lane < 8) pf[16 + ((lane - 4) >> 1) * 5 + (lane & 1)] = toth;
+      if (lane == 8) {
+        pb[18] = f1.x; pb[19] = w1b ? 1.0 : 0.0; pb[20] = has1 ? 1.0 : 0.0;
+        pb[23] = f2.x; pb[24] = w2b ? 1.0 : 0.0; pb[25] = has2 ? 1.0 : 0.0;
+      }
+      if (lane == 9) {
+        pf[18] = f1.y; pf[19] = w1f ? 1.0 : 0.0; pf[20] = has1 ? 1.0 : 0.0;
+        pf[23] = f2.y; pf[24] = w2f ? 1.0 : 0.0; pf[25] = has2 ? 1.0 : 0.0;
+      }
     }
-    if (lane == 9) {
-      pf[18] = f1.y; pf[19] = w1f ? 1.0 : 0.0; pf[20] = has1 ? 1.0 : 0.0;
-      pf[23] = f2.y; pf[24] = w2f ? 1.0 : 0.0; pf[25] = has2 ? 1.0 : 0.0;
+    // ---- passes 1, 2 (sticky parameters): lags 17 .. 32, 33 .. 48
+    for (uint32_t blk = 1; blk < nb; ++blk) {
+      double accb[LAGB], accf[LAGB];
+#pragma unroll
+      for (int l = 0; l < LAGB; ++l) { accb[l] = 0.0; accf[l] = 0.0; }
+      for (uint32_t ti = 0; ti < ntile; ++ti, ++seq) {
+        const uint32_t st = seq % M2_NST;
+        const uint32_t tile = wbase_s + st * (uint32_t)M2_STAGE;
+        mbar_wait(&full[st], (seq / M2_NST) & 1u);
+        const uint32_t rc = ra + ti * M2_ROWS + lane;
+        if (rc < rb) {
+          double2 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = m2_pair(tile, lane, k);
+          lag_block(std::false_type{}, tile, rc, 2u * blk, v, accb, accf);
+        }
+        __syncwarp();
+        if (lane == 0) issue_next();
+      }
+      const double totb = warp_reduce_16(accb);
+      const double totf = warp_reduce_16(accf);
+      if (lane < LAGB) {
+        pb[MO_VALS0 + (blk - 1) * LAGB + lane] = totb;
+        pf[MO_VALS0 + (blk - 1) * LAGB + lane] = totf;
+      }
     }
   }
 }
@@ -754,8 +835,11 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
   const double dn = (double)N, dh = (double)half;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  const bool ext = st.sticky[p] != 0;  // round 0 also holds lags 17 .. 48 of this parameter
   double vals[2 + LAGB];
   for (int k = 0; k < 2 + LAGB; ++k) vals[k] = 0.0;
+  double valx[LAG0X];
+  for (int k = 0; k < LAG0X; ++k) valx[k] = 0.0;
   for (uint32_t c = threadIdx.x; c < C; c += DEC_NT) {
     const double* pc = st.part + (((size_t)p * C + c) * g.nunits * 2 + kind) * MO_VALS;
     const double* y = reinterpret_cast<const double*>(zz + ((size_t)p * C + c) * N) + kind;
@@ -764,11 +848,14 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
     // one and all those first draws agree: its variance is then exactly 0 (diagnostics.py:196-201)
     bool k1 = true, k2 = true, seen1 = false, seen2 = false;
     double r1 = 0.0, r2 = 0.0;
-    double R[LAGB];
+    double R[LAGB], RX[LAG0X];
     for (int l = 0; l < LAGB; ++l) R[l] = 0.0;
+    for (int l = 0; l < LAG0X; ++l) RX[l] = 0.0;
     for (uint32_t u = 0; u < g.nunits; ++u) {
       const double* pu = pc + (size_t)u * 2 * MO_VALS;
       for (int l = 0; l < LAGB; ++l) R[l] += pu[l];
+      if (ext)
+        for (int l = 0; l < LAG0X; ++l) RX[l] += pu[MO_VALS0 + l];
       const double* sv = pu + LAGB;
       if (sv[4] != 0.0) {
         if (!seen1) { r1 = sv[2]; seen1 = true; }
@@ -807,10 +894,25 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
     }
     st.cmean[(size_t)item * C + c] = mf;
     st.csum[(size_t)item * C + c] = sum;
-    st.head[(size_t)item * C + c] = hs;
-    st.tail[(size_t)item * C + c] = ts;
+    // the work list a still unfinished item will be on starts at lag 17, or at lag 49 for a sticky parameter: the
+    // head / tail sums kept for it are those of ITS first uncovered lag
+    double hx = hs, tx = ts;
+    if (ext) {
+      for (int l = 0; l < LAG0X; ++l) {
+        const uint32_t t = 1 + LAGB + l;
+        if (t < N) {
+          hx += y[2 * (size_t)(t - 1)];
+          tx += y[2 * (size_t)(N - t)];
+          valx[l] += RX[l] - mf * (2.0 * sum - hx - tx) + (double)(N - t) * mf * mf;
+        }
+      }
+    }
+    st.head[(size_t)item * C + c] = ext ? hx : hs;
+    st.tail[(size_t)item * C + c] = ext ? tx : ts;
   }
   dec_reduce<DEC_NT>(vals, 2 + LAGB, red, tot);
+  __shared__ double totx[DEC_RED];
+  if (ext) dec_reduce<DEC_NT>(valx, LAG0X, red, totx);  // (uniform over the CTA)
   if (threadIdx.x == 0) {
     const size_t o = (size_t)kind * PB + p;
     // ---- R-hat on the 2C split chains of length half ----
@@ -849,18 +951,25 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
       } else {
         double rho_sum = 0.0;
         long long lag = (long long)N;
+        // an unfinished item goes on in the later rounds: from lag 17 (list 0, the first round's) or, with a sticky
+        // parameter's 48 lags behind it, from lag 49 (list 1, the second round's)
+        const int lst = ext ? 1 : 0;
         if (!st.geyer) {
-          if (rho_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, lag)) {
+          bool done = rho_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, lag);
+          if (!done && ext) done = rho_walk(totx, LAG0X, 1 + LAGB, N, C, var_hat, rho_sum, lag);
+          if (done) {
             st.ess[o] = (double)C * dn / (1.0 + 2.0 * rho_sum);
             st.lag[o] = lag;
           } else {
             st.varhat[item] = var_hat;
             st.rhosum[item] = rho_sum;
-            st.wl[0][atomicAdd(&st.nwl[0], 1)] = item;
+            st.wl[lst][atomicAdd(&st.nwl[lst], 1)] = item;
           }
         } else {
           double pend = 1.0, prev = inf;  // rho_0 := 1 opens the first pair
-          if (geyer_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, pend, prev, lag)) {
+          bool done = geyer_walk(tot + 2, LAGB, 1, N, C, var_hat, rho_sum, pend, prev, lag);
+          if (!done && ext) done = geyer_walk(totx, LAG0X, 1 + LAGB, N, C, var_hat, rho_sum, pend, prev, lag);
+          if (done) {
             st.ess[o] = geyer_ess((double)C * dn, rho_sum);
             st.lag[o] = lag;
           } else {
@@ -868,7 +977,7 @@ __global__ void __launch_bounds__(DEC_NT) k_decide0(const double2* __restrict__ 
             st.rhosum[item] = rho_sum;
             st.gpend[item] = pend;
             st.gprev[item] = prev;
-            st.wl[0][atomicAdd(&st.nwl[0], 1)] = item;
+            st.wl[lst][atomicAdd(&st.nwl[lst], 1)] = item;
           }
         }
       }
@@ -987,7 +1096,12 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_ess_rounds(const double2* __restr
   int cur = 0;
   for (uint32_t t0 = 1 + LAGB; t0 < g.N; t0 += LAGR, cur ^= 1) {
     const int nwork = __ldcg(&st.nwl[cur]);  // final since the barrier that ended the previous round
-    if (nwork == 0) break;                   // uniform over the grid
+    const bool first = t0 == 1u + LAGB;
+    if (nwork == 0) {                        // uniform over the grid
+      // the second round's list may already hold the sticky parameters' items (they start at lag 49, k_decide0)
+      if (first && __ldcg(&st.nwl[1]) > 0) continue;
+      break;
+    }
     const uint64_t total = (uint64_t)nwork * upi;
     const uint32_t lim = (g.N > t0) ? g.N - t0 : 0;  // first factors need i + t0 < N
     auto describe = [&](uint64_t w, R1Unit& un, uint32_t& u_out) {
@@ -1025,7 +1139,8 @@ __global__ void __launch_bounds__(MO_CTA, 2) k_ess_rounds(const double2* __restr
         moments_r_unit(S.m.r, un.zc, g, t0, un.kind, u, un.out, &S.bar, phase);
       }
     }
-    if (blockIdx.x == 0 && tid == 0) st.nwl[cur ^ 1] = 0;  // the list the decisions are about to build
+    // the list the decisions are about to build (the second round's was started by k_decide0: it is kept)
+    if (blockIdx.x == 0 && tid == 0 && !first) st.nwl[cur ^ 1] = 0;
     grid_barrier(gbar, target);
     for (int li = blockIdx.x; li < nwork; li += gridDim.x)
       decide_r_item<MO_CTA>(zz, g, PB, t0, cur, li, st, S.red, S.tot);

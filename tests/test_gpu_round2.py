@@ -394,6 +394,51 @@ def test_round0_tile_variant_chain_lengths(B, n):
         _check_vs_oracle(B, x, f"n={n} constant halves")
 
 
+
+def test_sticky_prediction_cannot_change_results(B):
+    """Round 0 covers 48 lags instead of 16 for the parameters whose FIRST chain looks sticky (k_predict_sticky); an
+    unfinished item then enters the later rounds at lag 49 (list 1) instead of lag 17 (list 0).  The guess may be
+    wrong in both directions and the two lists may be empty or not in any combination: R-hat, ESS and the truncation
+    lags must match the oracle in every case, alone and batched together, also with the Geyer truncation."""
+    from scipy.signal import lfilter
+
+    rng = np.random.default_rng(4949)
+    c, n = 6, 4096
+
+    def ar(phi, rows):
+        return lfilter([math.sqrt(1 - phi * phi)], [1.0, -phi], rng.standard_normal((rows, n)), axis=1)
+
+    all_sticky = ar(0.93, c)                                   # guessed sticky, needs more than 48 lags: list 1
+    first_only = np.concatenate([ar(0.95, 1), ar(0.0, c - 1)])  # guessed sticky, the pooled walk ends within a few lags
+    all_but_first = np.concatenate([ar(0.0, 1), ar(0.9, c - 1)])  # not guessed: list 0, rounds from lag 17
+    mild = ar(0.5, c)                                          # ends inside round 0 either way
+    very = ar(0.99, c)                                         # several later rounds
+    cases = {"all_sticky": all_sticky, "first_only": first_only, "all_but_first": all_but_first, "mild": mild, "very": very}
+    want = {k: O.diagnostics_param(v) for k, v in cases.items()}
+
+    def geyer_want(x):
+        _, z = O.rank_normalize(x)
+        _, zf = O.rank_normalize(O.fold_chains(x))
+        (wb, lb), (wt, lt) = O.ess_geyer(z, return_lag=True), O.ess_geyer(zf, return_lag=True)
+        return {"ess_bulk": wb, "ess_tail": wt, "lag_bulk": lb, "lag_tail": lt}
+
+    def check(names, geyer=False):
+        x = np.stack([cases[k] for k in names])
+        d = B.diagnostics_batch(x, ess_truncation="geyer") if geyer else B.diagnostics_batch(x)
+        for i, k in enumerate(names):
+            w = geyer_want(cases[k]) if geyer else want[k]
+            for key in ("ess_bulk", "ess_tail") if geyer else ("rhat", "ess_bulk", "ess_tail"):
+                assert close(float(d[key][i].item()), w[key], TOL), (names, k, key, float(d[key][i].item()), w[key])
+            assert int(d["lag_bulk"][i].item()) == w["lag_bulk"] and int(d["lag_tail"][i].item()) == w["lag_tail"], (names, k)
+
+    for k in cases:
+        check([k])                                   # one list empty, the other not (or both)
+    check(list(cases))                               # both lists in one launch
+    check(["all_but_first", "mild"])                 # only list 0
+    check(["all_sticky", "very", "first_only"])      # only list 1
+    check(list(cases), geyer=True)
+
+
 def test_ragged_chains_follow_the_reference(B):
     """Chains of different lengths (fixture from the unmodified reference, `make_ragged_golden.py`): pooled ranks over
     all draws, each chain split at its own midpoint, every (split) chain truncated to the shortest one."""

@@ -439,6 +439,20 @@ def test_sticky_prediction_cannot_change_results(B):
     check(list(cases), geyer=True)
 
 
+
+def test_randomised_shapes_against_the_oracle(B):
+    """`tools/fuzz_parity.py`: 1 .. 9 chains, chain lengths around the tile / sub-tile / split boundaries, ties,
+    constant stretches, sticky / anti-correlated / heavy-tailed chains, mixed batches -- R-hat, ESS, truncation lags and
+    quantiles against the oracle."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("fuzz_parity", Path(__file__).resolve().parent.parent / "tools" / "fuzz_parity.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(60, 7) == 0
+
+
 def test_ragged_chains_follow_the_reference(B):
     """Chains of different lengths (fixture from the unmodified reference, `make_ragged_golden.py`): pooled ranks over
     all draws, each chain split at its own midpoint, every (split) chain truncated to the shortest one."""

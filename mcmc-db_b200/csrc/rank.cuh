@@ -203,6 +203,30 @@ struct FoldView {
   // merge-path: number of left-part elements among the first o outputs (left first on ties)
   __device__ uint32_t split(uint32_t o) const {
     uint32_t lo = (o > nR()) ? o - nR() : 0, hi = min(o, nL());
+    // The predicate "L(a) <= R(o - 1 - a)" is true below the split and false from it on.  The two parts hold about
+    // the same share of every distance range, so the split lies near o * nL / M: bracket it from that guess with
+    // doubling steps before bisecting (6-8 dependent loads instead of ~18; same result, the predicate is monotone).
+    if (lo < hi) {
+      const uint32_t g = min(hi, max(lo, (uint32_t)(((uint64_t)o * nL()) / max(M, 1u))));
+      auto below = [&](uint32_t a) { return L(a) <= R(o - 1 - a); };  // a in [lo, hi)
+      if (g < hi && below(g)) {
+        uint32_t step = 16, a = g;  // the split is above g
+        lo = g + 1;
+        while (lo < hi) {
+          a = min(hi - 1, a + step);
+          if (below(a)) { lo = a + 1; step <<= 1; } else { hi = a; break; }
+          if (a == hi - 1) break;
+        }
+      } else {
+        uint32_t step = 16, a = g;  // the split is at or below g
+        hi = min(hi, g);
+        while (lo < hi) {
+          a = (a > lo + step) ? a - step : lo;
+          if (below(a)) { lo = a + 1; break; } else { hi = a; step <<= 1; }
+          if (a == lo) break;
+        }
+      }
+    }
     while (lo < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       if (L(mid) <= R(o - 1 - mid)) lo = mid + 1; else hi = mid;

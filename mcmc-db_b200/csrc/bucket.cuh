@@ -157,6 +157,54 @@ struct BucketBufs {
 };
 
 // ---------------------------------------------------------------- k_sample
+// Bitonic sort of 4096 keys held 8 per thread by 512 threads (element e = 8 * tid + r): strides below 8 are
+// compare-exchanges inside the thread, strides 8 .. 128 shuffles inside the warp (a warp holds 256 consecutive
+// elements), only the 10 stages with strides >= 256 go through shared memory -- the all-shared-memory network
+// measured L1-bound (89 %).  `s` holds the keys on entry and the sorted keys on return.
+__device__ __forceinline__ void sample_sort_4096(uint64_t* __restrict__ s) {
+  const uint32_t tid = threadIdx.x;
+  uint64_t k[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) k[r] = s[tid * 8 + r];
+#pragma unroll
+  for (uint32_t size = 2; size <= 4096; size <<= 1) {
+#pragma unroll
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 8) {
+        uint64_t q[8];
+        if (stride >= 256) {
+          __syncthreads();  // earlier partner reads are done
+#pragma unroll
+          for (int r = 0; r < 8; ++r) s[tid * 8 + r] = k[r];
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < 8; ++r) q[r] = s[((tid * 8) ^ stride) + r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) q[r] = __shfl_xor_sync(FULL, k[r], stride >> 3);
+        }
+        // ascending blocks keep the smaller key at the lower index
+        const bool keep_min = (((tid * 8) & stride) == 0) == (((tid * 8) & size) == 0);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) k[r] = keep_min ? min(k[r], q[r]) : max(k[r], q[r]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int r2 = r ^ (int)stride;
+          if (r2 > r) {
+            const bool up = (((tid * 8 + r) & size) == 0);
+            const uint64_t a = k[r], c = k[r2];
+            if ((a > c) == up) { k[r] = c; k[r2] = a; }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s[tid * 8 + r] = k[r];
+}
+
 __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, uint32_t M, BucketBufs b) {
   __shared__ uint64_t s[NB1_MAX * OVERSAMPLE];
   __shared__ int scell[NB1_MAX];
@@ -179,6 +227,9 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     s[j] = k;
   }
   __syncthreads();
+  if (S2 == 4096u) {  // (uniform; the usual case: 256 coarse buckets x 16 samples)
+    sample_sort_4096(s);
+  } else {
   // bitonic network.  With stride <= 32 the 32 pairs of a warp (in each of its passes over t) stay
   // inside one 64-element block that only this warp touches, so consecutive such steps need only
   // a warp barrier; a block barrier separates them from the wider steps.
@@ -196,6 +247,7 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
         if ((a > c) == up) { s[i] = c; s[j] = a; }
       }
     }
+  }
   }
   __syncthreads();
   const double lo = key2dbl(s[0]), hi = key2dbl(s[S - 1]);

@@ -33,6 +33,9 @@
 #ifndef B200REF_FIN_LOAD2
 #define B200REF_FIN_LOAD2 2
 #endif
+#ifndef B200REF_FIN_TAIL_UNROLL1
+#define B200REF_FIN_TAIL_UNROLL1 1
+#endif
 
 namespace b200ref {
 
@@ -1044,6 +1047,9 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
       less += (kt < k);
       le += (kt <= k);
     }
+#if B200REF_FIN_TAIL_UNROLL1
+#pragma unroll 1  // fine buckets beyond 4 draws are rare: no unrolled prologue / epilogue on the common zero-trip path
+#endif
     for (uint32_t t = a + 4; t < e; ++t) {
       const double kt = sm.kd[t];
       less += (kt < k);
@@ -1051,8 +1057,12 @@ __device__ __forceinline__ void finish_bucket(FinSmem<CAP, NF>& sm, const FineFn
     }
     const uint32_t eq = le - less;
     uint32_t eqb = 0;  // equal values in earlier slots: only tied draws need it
-    if (eq > 1u)
+    if (eq > 1u) {
+#if B200REF_FIN_TAIL_UNROLL1
+#pragma unroll 1
+#endif
       for (uint32_t t = a; t < s; ++t) eqb += (sm.kd[t] == k);
+    }
     const uint32_t i = B0 + a + less;
     const uint32_t pos = i + eqb;
     B200REF_CHECK(pos >= B0 && pos < B0 + n && (sm.i2[s] & ~TIED_BIT) < M, "finish_bucket: sorted position outside the bucket");

@@ -67,7 +67,8 @@ struct BucketFn {
   double cs;          // NCELL / (hi - lo), 0 if hi == lo
   double c0;          // sample median: centre for the shifted power sums
   double sp[NB1_MAX]; // sp[j], j = 0 .. nb1-2 : splitters (ascending); rest = +inf
-  uint16_t lut[NCELL + 2];  // lut[c] = number of splitters whose cell is < c
+  uint16_t lut[NCELL + 2];  // lut[c] = (splitters whose cell is < c) | (splitters whose cell is < c + 1) << 8: both ends of
+                            // cell c's splitter range (each <= 255) in one load
   int nb1;
   int sub;            // sub-buckets per coarse bucket (1: the coarse buckets are the buckets)
   double fsub[NB1_MAX];  // sub / (upper - lower) of coarse bucket c, 0 if degenerate
@@ -101,8 +102,9 @@ __device__ __forceinline__ int cell_of(double x, double lo, double cs) {
 __device__ __forceinline__ int coarse_of(double x, double lo, double cs, const double* __restrict__ sp,
                                          const uint16_t* __restrict__ lut) {
   const int c = cell_of(x, lo, cs);
-  int a = lut[c];
-  const int e = lut[c + 1];
+  const uint32_t ae = lut[c];
+  int a = (int)(ae & 0xffu);
+  const int e = (int)(ae >> 8);
   while (a < e && sp[a] <= x) ++a;
   return a;
 }
@@ -300,10 +302,13 @@ __global__ void __launch_bounds__(512) k_sample(const double* __restrict__ x, ui
     fn->fsub[j] = fsv;
   }
   for (int c = threadIdx.x; c < NCELL + 2; c += 512) {
-    // number of splitters with cell < c  (scell ascending over j < nb1-1, NCELL beyond)
+    // number of splitters with cell < c and with cell < c + 1  (scell ascending over j < nb1-1, NCELL beyond)
     int a = 0, e = nb1 - 1;
     while (a < e) { const int mid = (a + e) >> 1; if (scell[mid] < c) a = mid + 1; else e = mid; }
-    fn->lut[c] = (uint16_t)a;
+    int a1 = a;
+    e = nb1 - 1;
+    while (a1 < e) { const int mid = (a1 + e) >> 1; if (scell[mid] < c + 1) a1 = mid + 1; else e = mid; }
+    fn->lut[c] = (uint16_t)(a | (a1 << 8));
   }
   if (b.slab) {
     // Single-pass partition: capacity of every coarse bucket's slab.  A bucket holds M / nb1 draws on average with

@@ -74,8 +74,12 @@ def run(cases: int, seed: int) -> int:
             got = {key: float(d[key][i].item()) for key in ("rhat", "ess_bulk", "ess_tail")}
             ok = all(close(got[key], want[key], TOL) for key in got)
             # (no walk at all -- zero variance, one draw: the oracle reports lag 0 there, the device N)
-            for lk in ("lag_bulk", "lag_tail"):
-                ok = ok and (want[lk] == 0 or int(d[lk][i].item()) == want[lk])
+            # A correlation that is exactly zero in exact arithmetic (tiny symmetric inputs, e.g. one chain of 5 draws)
+            # gets its sign from the summation order: the walk may then stop one lag earlier or later with the SAME
+            # sum -- accepted only if the ESS agrees to 1e-12.
+            for lk, ek in (("lag_bulk", "ess_bulk"), ("lag_tail", "ess_tail")):
+                same = want[lk] == 0 or int(d[lk][i].item()) == want[lk]
+                ok = ok and (same or close(got[ek], want[ek], 1e-12))
             ns = O.numpy_stats(x[i].reshape(-1))
             ok = ok and all(float(d["quantiles"][i, j].item()) == ns[q] for j, q in enumerate(("q5", "q50", "q95")))
             if not ok:

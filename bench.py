@@ -223,6 +223,7 @@ def diag_measure(args, wname: str, rank: int, world: int, local: int, full: bool
         "config": make_config(w, world), "compare_passed": passed,
         "clocks": clocks, "gpu_launches": int(nl.item()), "pass_roofline": pass_roofline, "roofline": roofline,
     }
+    line["config"]["workspace_gb_cap"] = args.ws_gb  # caller-owned scratch: its size sets the number of parameter batches
     if not full or args.no_e2e:
         del cand, ref, ws
         torch.cuda.empty_cache()
@@ -529,7 +530,8 @@ def main() -> None:
     ap.add_argument("--glm-d", type=int, default=256)
     ap.add_argument("--glm-s", type=int, default=65_536)
     ap.add_argument("--glm-cpu-draws", type=int, default=512)
-    ap.add_argument("--ws-gb", type=float, default=32.0, help="cap of the device workspace")
+    ap.add_argument("--ws-gb", type=float, default=96.0,
+                    help="cap of the device workspace (the config-5 shard then runs in 4 parameter batches; 32 GB: 9 batches, +3 ms)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-draws-per-core", type=float, default=1.0e7,
                     help="cpu_baseline leg: draws each host core gets (sample = that many parameters)")
